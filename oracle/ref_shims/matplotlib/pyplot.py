@@ -1,0 +1,2 @@
+def __getattr__(name):
+    raise AttributeError(name)
