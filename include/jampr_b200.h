@@ -1,0 +1,196 @@
+/*
+ * jampr_b200.h — C ABI of libjampr_b200.so: the B200 (sm_100a) construction-rollout hot path of JAMPR+.
+ *
+ * The reference (jokofa/JAMPR_plus) has no FFI layer; its boundary for this path is two Python
+ * classes.  Each entry point below names the reference code it replaces, with
+ * file:line under /root/reference/.  The Python mirror classes in jampr_plus_b200/ (RPEnv, Policy)
+ * keep the reference signatures and call these functions through ctypes.
+ *
+ * Conventions
+ *  - Every pointer inside the structs is a DEVICE pointer owned by the caller (torch-allocated); the
+ *    library allocates nothing persistent, keeps no global state and never synchronises the stream.
+ *  - All calls enqueue work on `stream` (a cudaStream_t passed as void*) and return 0 on success,
+ *    a negative JAMPR_E_* code for argument errors, or a positive cudaError_t for launch errors.
+ *  - Data-dependent conditions the reference raises on are OR-ed into `status[rollout]`
+ *    (JAMPR_ST_*), the caller turns them into the reference's RuntimeError / RuntimeWarning.
+ *  - Rollout index b = instance * num_samples + sample (reference env.py:1189-1202 ordering).
+ */
+#ifndef JAMPR_B200_H
+#define JAMPR_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define JAMPR_API __attribute__((visibility("default")))
+#else
+#define JAMPR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JAMPR_ABI_VERSION 1
+
+/* argument errors */
+#define JAMPR_E_BADARG   (-1)
+#define JAMPR_E_TOOLARGE (-2)   /* graph does not fit the on-chip tile of this build */
+#define JAMPR_E_UNSUPPORTED (-3)
+
+/* per-rollout status bits */
+#define JAMPR_ST_NO_FEASIBLE     1   /* env.py:1020-1021 "no feasible nodes left" (RuntimeError)  */
+#define JAMPR_ST_TOUR_OVERFLOW   2   /* env.py:230-236 tour buffer (64 slots) exceeded (RuntimeError) */
+#define JAMPR_ST_FLEET_EXHAUSTED 4   /* env.py:254-258 "used all available vehicles!" (RuntimeWarning) */
+#define JAMPR_ST_NAN_LOGITS      8   /* policy.py:208 "Logits contain NANs!" (AssertionError) */
+#define JAMPR_ST_TW_COLLAPSE    16   /* env.py:408 assertion in the time-window fix-up (per instance) */
+
+/* decode types (policy.py:229-240) */
+#define JAMPR_DECODE_GREEDY   0
+#define JAMPR_DECODE_SAMPLING 1
+
+/* control block on the device: int32[JAMPR_CTL_WORDS].  The step counter env._step (env.py:139,309)
+ * is host-known and travels as a launch argument; only data-dependent words live here. */
+#define JAMPR_CTL_N_ALLVIS    0   /* rollouts whose customers are all visited */
+#define JAMPR_CTL_DONE_STEP   1   /* value of env._step at which the episode terminated (env.py:281), -1 = running */
+#define JAMPR_CTL_WORDS       8
+
+typedef struct {
+  int32_t n_inst;        /* I: instances */
+  int32_t n_samples;     /* P: rollouts per instance (env.num_samples) */
+  int32_t n_nodes;       /* N: graph size incl. depot */
+  int32_t n_slots;       /* K: max_concurrent_vehicles */
+  int32_t k_nbh;         /* k: ceil(k_nbh_frac * N) (graph_utils.py:99) */
+  int32_t k_max;         /* K_max: int(kv + floor(ln kv)) (env.py:362) */
+  int32_t plan_len;      /* L: min(64, N) (env.py:165) */
+  int32_t upd_step;      /* tour_graph_update_step (env.py:43) */
+} jampr_dims_t;
+
+/* Static data, once per INSTANCE (the reference replicates it per sample, env.py:1189-1202). */
+typedef struct {
+  const float* coords;     /* in  (I,N,2)  */
+  const float* demand;     /* in  (I,N)    */
+  float*       tw;         /* in/out (I,N,2): window ends shrunk where return is impossible (env.py:395-409) */
+  const float* service;    /* in  (I)      */
+  const float* horizon;    /* in  (I) org_service_horizon */
+  float*       dist;       /* out (I,N,N) floor(10*||100 dx||)/10/horizon (challenge_utils.py:35, env.py:916-922) */
+  float*       ttd;        /* out (I,N) time to depot = dist[:,:,0] */
+  int16_t*     knn;        /* out (I,N,k) row u>=1: k-1 nearest customers incl. u, then depot (graph_utils.py:113-136) */
+  float*       knn_w;      /* out (I,N,k) dist[u, knn[u,j]] */
+  int16_t*     order;      /* out (I,N) nodes by Euclidean distance to depot (env.py:855-861) */
+  int32_t*     inst_status;/* out (I) JAMPR_ST_TW_COLLAPSE */
+  float*       static_emb; /* out (I,N,256) node-encoder output (node_encoder.py:128-155) */
+  float*       h0;         /* out (I,N,128) node_emb_input_proj(static_emb) (tour_encoder.py:170-172), hoisted */
+} jampr_instances_t;
+
+/* Episode state, once per ROLLOUT (bs = I*P). SoA, all arrays contiguous. */
+typedef struct {
+  uint8_t*  visited;   /* (bs,N)        env._visited */
+  int16_t*  pred;      /* (bs,N)        predecessor along the tour row (0 = depot) — tour graph, env.py:804-835 */
+  int16_t*  succ;      /* (bs,N)        successor along the tour row (0 = depot / none yet) */
+  int16_t*  plan;      /* (bs,K_max,L)  env.tour_plan */
+  uint8_t*  vflags;    /* (bs,K_max)    bit0 active_vehicles, bit1 _finished */
+  int32_t*  row;       /* (bs,K)        env.active_to_plan_idx */
+  int32_t*  nxt;       /* (bs,K)        env.next_index_in_tour */
+  int32_t*  cur;       /* (bs,K)        env.cur_node */
+  int32_t*  row_last;  /* (bs,K)        last customer written to the slot's tour row */
+  float*    cap;       /* (bs,K)        env.cur_cap */
+  float*    time;      /* (bs,K)        env.cur_time */
+  float*    cttd;      /* (bs,K)        env.cur_time_to_depot */
+  float*    total;     /* (bs)          env._total */
+  float*    cost;      /* (bs)          cost of the last step (return value of env.step) */
+  int32_t*  status;    /* (bs)          JAMPR_ST_* */
+  uint8_t*  allvis;    /* (bs)          all customers visited */
+  int32_t*  nvis;      /* (bs)          number of visited customers */
+  int16_t*  nbh;       /* (bs,K,k)      obs.nbh */
+  uint8_t*  mask;      /* (bs,K,k)      obs.nbh_mask (1 = infeasible) */
+  int32_t*  action;    /* (bs,2)        (slot, node) chosen by the policy */
+  float*    ll;        /* (bs)          log-likelihood of the chosen action */
+  float*    entropy;   /* (bs)          entropy of the action distribution (sampling) */
+  float*    logp;      /* (bs,K*k) or NULL: full log-probabilities (parity / training) */
+  float*    h_fin;     /* (bs,N,128)    tour-graph node embedding of the last refresh (tour_encoder.py:198 cache) */
+  float*    ne;        /* (bs,N,256)    node_emb = node_emb_output_proj(h) + static_emb (tour_encoder.py:217-218) */
+  float*    ne_stats;  /* (bs,2,256)    column mean and max of ne over the N nodes (policy.py:179-181) */
+  int32_t*  ctl;       /* (JAMPR_CTL_WORDS) control block */
+} jampr_state_t;
+
+/* Policy weights: one fp32 blob on the device, packed by jampr_plus_b200/model/packing.py.
+ * Offsets (in floats) are given by jampr_weight_offsets(). */
+#define JAMPR_PREC_F32  0   /* fp32 CUDA-core path: the 1e-5 parity anchor */
+#define JAMPR_PREC_BF16 1   /* bf16 tcgen05 tensor-core GEMMs, fp32 accumulate and epilogues */
+
+typedef struct {
+  const float* blob;       /* fp32 blob, layout = jampr_weight_offsets() */
+  int64_t      n_floats;
+  const void*  blob_bf16;  /* bf16 GEMM operands in UMMA tile order (packing.py), or NULL */
+  int64_t      n_bf16;
+  int32_t      precision;  /* JAMPR_PREC_* */
+  int32_t      reserved;
+} jampr_weights_t;
+
+JAMPR_API int jampr_abi_version(void);
+
+/* Number of floats of the packed weight blob and the offset table (names in packing.py).
+ * Replaces nothing in the reference; it is the checkpoint -> device contract. */
+JAMPR_API int64_t jampr_weight_blob_floats(void);
+JAMPR_API int jampr_weight_offsets(int64_t* out, int32_t max_entries);
+
+/* RPEnv.load_data static part: distance matrix, window fix-up, kNN table, depot order.
+ * Replaces env.py:369-409 and the per-instance Python loop env.py:782-794 (+ graph_utils.py:104-141). */
+JAMPR_API int jampr_setup_instances(const jampr_dims_t* d, const jampr_instances_t* inst, void* stream);
+
+/* NodeEncoder.forward, once per instance (node_encoder.py:128-155), plus the hoisted
+ * node_emb_input_proj (tour_encoder.py:170-172). */
+JAMPR_API int jampr_node_encoder(const jampr_dims_t* d, const jampr_instances_t* inst,
+                       const jampr_weights_t* w, void* stream);
+
+/* RPEnv.reset (env.py:146-201).  start_nodes: (bs, n_start) int32 forced first moves, one per
+ * vehicle slot 0..n_start-1 (the POMO pseudo-steps, env.py:1271-1297), or NULL / n_start = 0.
+ * Leaves the first observation (nbh, mask) in the state. */
+JAMPR_API int jampr_env_reset(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_state_t* st,
+                    const int32_t* start_nodes, int32_t n_start, void* stream);
+
+/* RPEnv.step (env.py:203-311) on st->action (or `action` if not NULL, (bs,2) int32): transition,
+ * tour buffers, vehicle hand-over, termination incl. _return_all and singleton penalties
+ * (env.py:281-295, 1133-1170), then the next observation (env.py:848-1022).  step_no = env._step
+ * before the call.  After termination (ctl[DONE_STEP] >= 0 from an earlier call) it is a no-op. */
+JAMPR_API int jampr_env_step(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_state_t* st,
+                   const int32_t* action, int32_t step_no, void* stream);
+
+/* RPEnv.import_sol tail (env.py:681-706): state arrays were filled by the caller from solution
+ * lists (plan, vflags, row, nxt, cur, cap, time, cttd, total); derives visited/pred/succ/row_last
+ * from the tour buffers, writes max_b(visited + finished) (env.py:704) to *max_step_out (device int32)
+ * and produces the observation. */
+JAMPR_API int jampr_env_import_finish(const jampr_dims_t* d, const jampr_instances_t* inst,
+                            const jampr_state_t* st, int32_t* max_step_out, void* stream);
+
+/* Policy.forward for one step (policy.py:120-227; tour_encoder.py:159-243; attn_decoder.py:62-98):
+ * tour-graph GNN (or cached embedding), tour embeddings, pointer attention, masked log-softmax,
+ * greedy argmax or inverse-CDF sampling.  graph_fresh: 1 = rebuild the tour-graph embedding,
+ * 0 = reuse st->h_fin / st->ne (the rule of env.py:801 evaluated by the caller).  uniforms: (bs) floats in [0,1) or NULL to draw them from
+ * the counter-based generator keyed by (seed, rollout, step). */
+JAMPR_API int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                      const jampr_state_t* st, int32_t graph_fresh, int32_t step_no,
+                      int32_t decode_type, uint64_t seed, const float* uniforms, void* stream);
+
+/* The whole `while not done: action = policy(obs); obs = env.step(action)` loop
+ * (training.py:72-77, lns.py:258-261) enqueued without host round trips: at most max_steps
+ * iterations starting at env._step = first_step; kernels turn into no-ops once the device-side
+ * done word is set.  Returns the number of iterations enqueued (>= 0) or an error (< 0). */
+JAMPR_API int jampr_rollout(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                  const jampr_state_t* st, int32_t first_step, int32_t first_fresh,
+                  int32_t decode_type, uint64_t seed, int32_t max_steps, void* stream);
+
+/* Best-of-samples reduction (training.py:80-94): per instance argmin of total cost over its P
+ * rollouts; copies that rollout's tour buffer.  best_cost (I), best_idx (I), best_plan (I,K_max,L). */
+JAMPR_API int jampr_gather_best(const jampr_dims_t* d, const jampr_state_t* st, float* best_cost,
+                      int32_t* best_idx, int16_t* best_plan, void* stream);
+
+/* Batch-independent cost of the tours in the buffers: travel + waiting + service per tour incl. the
+ * return leg, + 2*time_to_depot per unvisited customer (logic of env.py:708-718, 287-295). */
+JAMPR_API int jampr_true_cost(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_state_t* st,
+                    float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAMPR_B200_H */

@@ -1,0 +1,78 @@
+// Host-side orchestration of the policy step and of the whole construction rollout (C ABI).
+// Nothing here synchronises: every call only enqueues kernels on the caller's stream, so a rollout can be
+// captured into a CUDA graph by the caller.  Termination is data dependent (env.py:281) and lives in the
+// device control block; kernels launched after the terminating step return immediately.
+#include "common.cuh"
+
+int jampr_node_encoder_f32(const jampr_dims_t*, const jampr_instances_t*, const float*, cudaStream_t);
+int jampr_tour_encoder_f32(const jampr_dims_t*, const jampr_instances_t*, const jampr_state_t*, const float*, int,
+                           cudaStream_t);
+int jampr_decoder_launch(const jampr_dims_t*, const jampr_instances_t*, const jampr_state_t*, const float*, int, int,
+                         uint64_t, const float*, cudaStream_t);
+int jampr_node_encoder_tc(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, cudaStream_t);
+int jampr_tour_encoder_tc(const jampr_dims_t*, const jampr_instances_t*, const jampr_state_t*,
+                          const jampr_weights_t*, int, cudaStream_t);
+
+static int check_policy_args(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w) {
+  if (!d || !inst || !w || !w->blob || w->n_floats < (int64_t)OFF_END) return JAMPR_E_BADARG;
+  if (d->n_inst <= 0 || d->n_samples <= 0 || d->n_nodes < 2 || d->n_slots <= 0 || d->n_slots > JAMPR_MAX_SLOTS ||
+      d->k_nbh < 2 || d->k_nbh > d->n_nodes)
+    return JAMPR_E_BADARG;
+  if (w->precision != JAMPR_PREC_F32 && w->precision != JAMPR_PREC_BF16) return JAMPR_E_BADARG;
+  if (w->precision == JAMPR_PREC_BF16 && !w->blob_bf16) return JAMPR_E_BADARG;
+  return 0;
+}
+
+extern "C" int64_t jampr_weight_blob_floats(void) { return (int64_t)OFF_END; }
+
+extern "C" int jampr_weight_offsets(int64_t* out, int32_t max_entries) {
+  static const int64_t offs[] = {OFF_NE_IN_WT, OFF_NE_IN_B, OFF_NE_BLK, OFF_NE_OUT_WT, OFF_NE_OUT_B, OFF_TE_IN_WT,
+                                 OFF_TE_IN_B, OFF_TE_BLK, OFF_TE_OUT_WT, OFF_TE_OUT_B, OFF_TF_WT, OFF_TF_B,
+                                 OFF_TO_WT, OFF_TO_B, OFF_CTXT_WT, OFF_GK_W, OFF_GV_WT, OFF_LK_W, OFF_OUT_WT,
+                                 OFF_END, BLK_FLOATS};
+  const int n = (int)(sizeof(offs) / sizeof(offs[0]));
+  if (!out || max_entries < n) return JAMPR_E_BADARG;
+  for (int i = 0; i < n; ++i) out[i] = offs[i];
+  return n;
+}
+
+extern "C" int jampr_node_encoder(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                                  void* stream) {
+  const int rc = check_policy_args(d, inst, w);
+  if (rc) return rc;
+  if (w->precision == JAMPR_PREC_BF16) return jampr_node_encoder_tc(d, inst, w, (cudaStream_t)stream);
+  return jampr_node_encoder_f32(d, inst, w->blob, (cudaStream_t)stream);
+}
+
+extern "C" int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                                 const jampr_state_t* st, int32_t graph_fresh, int32_t step_no, int32_t decode_type,
+                                 uint64_t seed, const float* uniforms, void* stream) {
+  int rc = check_policy_args(d, inst, w);
+  if (rc) return rc;
+  if (!st || (decode_type != JAMPR_DECODE_GREEDY && decode_type != JAMPR_DECODE_SAMPLING)) return JAMPR_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (graph_fresh) {
+    rc = (w->precision == JAMPR_PREC_BF16) ? jampr_tour_encoder_tc(d, inst, st, w, step_no, s)
+                                           : jampr_tour_encoder_f32(d, inst, st, w->blob, step_no, s);
+    if (rc) return rc;
+  }
+  return jampr_decoder_launch(d, inst, st, w->blob, step_no, decode_type, seed, uniforms, s);
+}
+
+extern "C" int jampr_rollout(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                             const jampr_state_t* st, int32_t first_step, int32_t first_fresh, int32_t decode_type,
+                             uint64_t seed, int32_t max_steps, void* stream) {
+  int rc = check_policy_args(d, inst, w);
+  if (rc) return rc;
+  if (!st || first_step < 0 || d->upd_step <= 0) return JAMPR_E_BADARG;
+  const int cap = d->n_nodes + d->k_max + 1;   // last admissible value of env._step (env.py:281)
+  int fresh = first_fresh, n = 0;
+  for (int step = first_step; step <= cap && n < max_steps; ++step, ++n) {
+    rc = jampr_policy_step(d, inst, w, st, fresh, step, decode_type, seed, nullptr, stream);
+    if (rc) return rc > 0 ? -1000 - rc : rc;
+    rc = jampr_env_step(d, inst, st, nullptr, step, stream);
+    if (rc) return rc > 0 ? -1000 - rc : rc;
+    fresh = (step <= d->n_slots + 1) || (step % d->upd_step == 0);   // env.py:801 with the pre-increment _step
+  }
+  return n;
+}

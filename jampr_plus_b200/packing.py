@@ -1,0 +1,72 @@
+"""Checkpoint state_dict -> device weight blob(s) consumed by libjampr_b200.so.
+
+The fp32 blob layout is owned by the library (csrc/common.cuh, queried through jampr_weight_offsets);
+GEMM operands are stored K-major ("WT": row = input feature) so that kernels stream them row by row."""
+from typing import Dict
+
+import torch
+
+from . import _cabi
+from .weights import canonical_key, state_dict_schema
+
+
+def validate_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Canonical key names (older PyG lin_l/lin_r aliases accepted), exact schema check (fails loudly)."""
+    schema = state_dict_schema()
+    out = {canonical_key(k): v for k, v in sd.items()}
+    missing = [k for k in schema if k not in out]
+    extra = [k for k in out if k not in schema]
+    if missing or extra:
+        raise KeyError(f"state_dict does not match the gnn_attn policy schema: missing={missing} unexpected={extra}")
+    for k, shape in schema.items():
+        if tuple(out[k].shape) != tuple(shape):
+            raise ValueError(f"{k}: expected shape {tuple(shape)}, got {tuple(out[k].shape)}")
+    return out
+
+
+def _block(sd, prefix: str) -> torch.Tensor:
+    wt = torch.cat((sd[f"{prefix}.conv.lin_rel.weight"].t(), sd[f"{prefix}.conv.lin_root.weight"].t()), 0)  # (256,128)
+    return torch.cat((wt.reshape(-1), sd[f"{prefix}.conv.lin_rel.bias"], sd[f"{prefix}.norm.weight"],
+                      sd[f"{prefix}.norm.bias"]))
+
+
+def pack_f32(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """CPU fp32 blob in the layout of csrc/common.cuh."""
+    sd = {k: v.detach().to(torch.float32).cpu() for k, v in validate_state_dict(sd).items()}
+    off = _cabi.weight_offsets()
+    blob = torch.zeros(off["END"], dtype=torch.float32)
+
+    def put(name, t):
+        t = t.contiguous().reshape(-1)
+        blob[off[name]: off[name] + t.numel()] = t
+
+    def halves(w):  # (256, K) -> [2][K][128]: column halves of W^T
+        wt = w.t()  # (K, 256)
+        return torch.stack((wt[:, :128], wt[:, 128:]), 0)
+
+    w_in = torch.zeros(8, 128)
+    w_in[:7] = sd["node_encoder.input_proj.weight"].t()
+    put("NE_IN_WT", w_in)
+    put("NE_IN_B", sd["node_encoder.input_proj.bias"])
+    put("NE_BLK", torch.cat([_block(sd, f"node_encoder.layers.{i}") for i in range(3)]))
+    put("NE_OUT_WT", halves(sd["node_encoder.output_proj.weight"]))
+    put("NE_OUT_B", sd["node_encoder.output_proj.bias"])
+    put("TE_IN_WT", sd["tour_encoder.node_emb_input_proj.weight"].t())
+    put("TE_IN_B", sd["tour_encoder.node_emb_input_proj.bias"])
+    put("TE_BLK", torch.cat([_block(sd, f"tour_encoder.tour_layers.{i}") for i in range(3)]
+                            + [_block(sd, f"tour_encoder.rev_tour_layers.{i}") for i in range(3)]))
+    put("TE_OUT_WT", halves(sd["tour_encoder.node_emb_output_proj.weight"]))
+    put("TE_OUT_B", sd["tour_encoder.node_emb_output_proj.bias"])
+    w_tf = torch.zeros(8, 128)
+    w_tf[:5] = sd["tour_encoder.input_proj.weight"].t()
+    put("TF_WT", w_tf)
+    put("TF_B", sd["tour_encoder.input_proj.bias"])
+    put("TO_WT", sd["tour_encoder.output_proj.weight"].t())
+    put("TO_B", sd["tour_encoder.output_proj.bias"])
+    put("CTXT_WT", sd["decoder.ctxt_proj.weight"].t())
+    sp = sd["decoder.set_proj.weight"]
+    put("GK_W", sp[0:256])
+    put("GV_WT", sp[256:512].t())
+    put("LK_W", sp[512:768])
+    put("OUT_WT", sd["decoder.out_proj.weight"].t())
+    return blob
