@@ -80,6 +80,9 @@ typedef struct {
   int32_t*     inst_status;/* out (I) JAMPR_ST_TW_COLLAPSE */
   float*       static_emb; /* out (I,N,256) node-encoder output (node_encoder.py:128-155) */
   float*       h0;         /* out (I,N,128) node_emb_input_proj(static_emb) (tour_encoder.py:170-172), hoisted */
+  const float* dist_given; /* in  (I,N,N) or NULL: caller-supplied normalised transit matrix copied into `dist`
+                              instead of evaluating the DIMACS formula (e.g. a matrix computed by torch on the
+                              host: MKL's vsSqrt is not correctly rounded, sqrtf on the device is) */
 } jampr_instances_t;
 
 /* Episode state, once per ROLLOUT (bs = I*P). SoA, all arrays contiguous. */
@@ -171,6 +174,12 @@ JAMPR_API int jampr_env_import_finish(const jampr_dims_t* d, const jampr_instanc
 JAMPR_API int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
                       const jampr_state_t* st, int32_t graph_fresh, int32_t step_no,
                       int32_t decode_type, uint64_t seed, const float* uniforms, void* stream);
+
+/* The per-step tour-graph GNN alone (tour_encoder.py:159-198 + the node_emb projection :217-218): what
+ * jampr_policy_step runs when graph_fresh = 1.  Exposed so that callers (tests, bench.py) can check and
+ * time the dominant kernel in isolation. */
+JAMPR_API int jampr_tour_encoder(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                       const jampr_state_t* st, int32_t step_no, void* stream);
 
 /* The whole `while not done: action = policy(obs); obs = env.step(action)` loop
  * (training.py:72-77, lns.py:258-261) enqueued without host round trips: at most max_steps

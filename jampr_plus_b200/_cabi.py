@@ -28,7 +28,7 @@ class Dims(C.Structure):
 class Instances(C.Structure):
     _fields_ = [(n, _p) for n in
                 ("coords", "demand", "tw", "service", "horizon", "dist", "ttd", "knn", "knn_w", "order",
-                 "inst_status", "static_emb", "h0")]
+                 "inst_status", "static_emb", "h0", "dist_given")]
 
 
 STATE_FIELDS = ("visited", "pred", "succ", "plan", "vflags", "row", "nxt", "cur", "row_last", "cap", "time", "cttd",
@@ -47,7 +47,7 @@ class Weights(C.Structure):
 
 SYMBOLS = ("jampr_abi_version", "jampr_weight_blob_floats", "jampr_weight_offsets", "jampr_setup_instances",
            "jampr_node_encoder", "jampr_env_reset", "jampr_env_step", "jampr_env_import_finish",
-           "jampr_policy_step", "jampr_rollout", "jampr_gather_best", "jampr_true_cost")
+           "jampr_tour_encoder", "jampr_policy_step", "jampr_rollout", "jampr_gather_best", "jampr_true_cost")
 
 _lib = None
 
@@ -70,6 +70,7 @@ def load_library():
     lib.jampr_env_reset.argtypes = [PD, PI, PS, _p, C.c_int32, _p]
     lib.jampr_env_step.argtypes = [PD, PI, PS, _p, C.c_int32, _p]
     lib.jampr_env_import_finish.argtypes = [PD, PI, PS, _p, _p]
+    lib.jampr_tour_encoder.argtypes = [PD, PI, PW, PS, C.c_int32, _p]
     lib.jampr_policy_step.argtypes = [PD, PI, PW, PS, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _p, _p]
     lib.jampr_rollout.argtypes = [PD, PI, PW, PS, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, _p]
     lib.jampr_gather_best.argtypes = [PD, PS, _p, _p, _p, _p]
@@ -90,7 +91,7 @@ def check(rc: int, what: str) -> int:
         if rc <= -1000:
             raise RuntimeError(f"{what}: CUDA launch error {-rc - 1000}")
         raise RuntimeError(f"{what}: {ERRORS.get(rc, rc)}")
-    if rc > 0 and what != "jampr_rollout":
+    if rc > 0 and what not in ("jampr_rollout", "jampr_weight_offsets"):
         raise RuntimeError(f"{what}: CUDA error {rc}")
     return rc
 

@@ -44,12 +44,23 @@ extern "C" int jampr_node_encoder(const jampr_dims_t* d, const jampr_instances_t
   return jampr_node_encoder_f32(d, inst, w->blob, (cudaStream_t)stream);
 }
 
+extern "C" int jampr_tour_encoder(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                                  const jampr_state_t* st, int32_t step_no, void* stream) {
+  const int rc = check_policy_args(d, inst, w);
+  if (rc) return rc;
+  if (!st || !st->h_fin || !st->ne || !st->ne_stats) return JAMPR_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  return (w->precision == JAMPR_PREC_BF16) ? jampr_tour_encoder_tc(d, inst, st, w, step_no, s)
+                                           : jampr_tour_encoder_f32(d, inst, st, w->blob, step_no, s);
+}
+
 extern "C" int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
                                  const jampr_state_t* st, int32_t graph_fresh, int32_t step_no, int32_t decode_type,
                                  uint64_t seed, const float* uniforms, void* stream) {
   int rc = check_policy_args(d, inst, w);
   if (rc) return rc;
   if (!st || (decode_type != JAMPR_DECODE_GREEDY && decode_type != JAMPR_DECODE_SAMPLING)) return JAMPR_E_BADARG;
+  if (!st->h_fin || !st->ne || !st->ne_stats) return JAMPR_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (graph_fresh) {
     rc = (w->precision == JAMPR_PREC_BF16) ? jampr_tour_encoder_tc(d, inst, st, w, step_no, s)

@@ -20,7 +20,12 @@ __global__ void __launch_bounds__(256) setup_instances_kernel(jampr_dims_t d, ja
   __syncthreads();
   const float hz = p.horizon[i];
   float* dist = p.dist + (size_t)i * N * N;
+  const float* given = p.dist_given ? p.dist_given + (size_t)i * N * N : nullptr;
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    if (given) {
+      dist[e] = given[e];
+      continue;
+    }
     const int u = e / N, v = e - u * N;
     const float dx = __fmul_rn(100.0f, __fsub_rn(cx[u], cx[v]));
     const float dy = __fmul_rn(100.0f, __fsub_rn(cy[u], cy[v]));

@@ -1,0 +1,63 @@
+"""Whole construction rollouts without host round trips.
+
+``rollout()`` replaces the reference's Python loop ``while not done: action = policy(obs); obs = env.step(action)``
+(``lib/model/training.py:72-77``, ``lib/lns/lns.py:258-261``) by one ``jampr_rollout`` call that enqueues every
+step on the current stream; termination lives in a device control word.  ``eval_episode`` mirrors
+``training.py:54-96`` (best-of-samples reduction included)."""
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _cabi
+from .routing.formats import RPInstance
+
+__all__ = ["rollout", "eval_episode"]
+
+
+def rollout(policy, env, max_steps: Optional[int] = None, check: bool = True) -> Tuple[torch.Tensor, Dict]:
+    """Run the episode currently held by ``env`` (after reset() / import_sol()) to termination on the device.
+
+    Returns (total cost (bs,), info) with the reference's info keys."""
+    assert env._is_reset, "call env.reset() or env.import_sol() first"
+    st = env.state
+    st.ensure_policy_buffers(policy.return_logp)
+    w = policy.encode_static(env)
+    cap = env.graph_size + env.max_vehicle_number + 1
+    n = cap - env._step + 1 if max_steps is None else max_steps
+    rc = policy._lib.jampr_rollout(env._dims, env._inst, w, st.struct(), int(env._step), int(env._graph_fresh),
+                                   policy._decode_code(), int(policy.sampling_seed), int(n), env._stream())
+    _cabi.check(rc, "jampr_rollout")
+    info: Dict = {}
+    if check:
+        done_step = int(st["ctl"][_cabi.CTL_DONE_STEP].item())      # the one device->host sync of the rollout
+        env._raise_status()
+        if done_step >= 0:
+            env._step = done_step + 1
+            env._has_instance = False
+            env._is_reset = False
+            env._done = True
+        else:
+            env._step += rc
+        info = {"done_step": done_step, "steps_enqueued": rc}
+    return st["total"], info
+
+
+def eval_episode(data: List[RPInstance], env, policy, sampling: bool = False, **kwargs):
+    """One evaluation episode (training.py:54-96): returns (cost per instance, info)."""
+    policy.eval()
+    policy.set_decode_type("sampling" if sampling and not env.pomo else "greedy")
+    policy.reset_static()
+    env.load_data(data)
+    env.reset()
+    total, info = rollout(policy, env)
+    info["current_total_cost"] = total.cpu().numpy()
+    info["k_used"] = env.k_used.cpu().numpy()
+    costs = total.cpu()
+    if env.num_samples > 1:
+        best_cost, best_idx, _ = env.gather_best()
+        bi = best_idx.long().cpu()
+        rng = torch.arange(bi.numel())
+        info = {k: (v.reshape(-1, env.num_samples)[rng.numpy(), bi.numpy()] if hasattr(v, "reshape") else v)
+                for k, v in info.items()}
+        costs = best_cost.cpu()
+    return costs, info

@@ -1,0 +1,217 @@
+"""JAMPR policy on the B200: host-side mirror of the reference ``lib.model.Policy``.
+
+Same constructor, ``forward(obs) -> (action, log_lik, entropy)``, ``reset_static`` and
+``set_decode_type`` as reference ``lib/model/policy.py:36-240``, and the same ``state_dict`` key schema
+(``tests/golden/state_dict_schema.json``, checked against the reference module), so shipped checkpoints
+load with ``load_state_dict`` unchanged.  The modules below only *hold parameters*: the forward pass is
+the CUDA library (node encoder, per-step tour-graph encoder, fused pointer decoder).  Supported
+architecture: ``config/policy/gnn_attn.yaml`` (the one every shipped checkpoint uses); anything else raises.
+"""
+from typing import Dict, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import _cabi
+from ..packing import pack_bf16, pack_f32
+from ..routing.formats import RPObs
+
+__all__ = ["Policy", "GNN_ATTN_POLICY_CFG"]
+
+# config/policy/gnn_attn.yaml:5-38
+GNN_ATTN_POLICY_CFG = {
+    "embedding_dim": 256,
+    "node_encoder_type": "NodeEncoder",
+    "node_encoder_args": {"hidden_dim": 128, "num_layers": 3, "conv_type": "GraphConv", "activation": "gelu",
+                          "skip": True, "norm_type": "ln", "add_linear": False},
+    "tour_encoder_type": "TourEncoder",
+    "tour_encoder_args": {"hidden_dim": 128, "num_layers": 2, "propagate_reverse": True, "consolidate_nbh": True,
+                          "conv_type": "GraphConv", "activation": "gelu", "skip": True, "norm_type": "ln",
+                          "add_linear": False},
+    "decoder_type": "AttnDecoder",
+    "decoder_args": {"hidden_dim": 256, "num_heads": 4, "clip_tanh": 10.0, "bias": False},
+}
+
+
+def _check_cfg(name: str, got: Optional[Dict], want: Dict):
+    got = dict(want if got is None else got)
+    for key, val in got.items():
+        if key in want and want[key] != val:
+            raise NotImplementedError(f"{name}.{key}={val!r}: the CUDA path implements {want[key]!r} "
+                                      f"(config/policy/gnn_attn.yaml)")
+        if key not in want and key not in ("dropout", "aggr"):
+            raise NotImplementedError(f"{name}.{key} is not supported by the CUDA path")
+    if got.get("aggr", "max") != "max":
+        raise NotImplementedError("only max aggregation (graph_conv.py:39) is implemented")
+
+
+class _Conv(nn.Module):          # PyG GraphConv parameter layout: lin_rel (bias), lin_root (no bias)
+    def __init__(self, h):
+        super().__init__()
+        self.lin_rel = nn.Linear(h, h, bias=True)
+        self.lin_root = nn.Linear(h, h, bias=False)
+
+
+class _Block(nn.Module):         # graph_conv.py:25-64
+    def __init__(self, h):
+        super().__init__()
+        self.conv = _Conv(h)
+        self.norm = nn.LayerNorm(h)
+
+
+class _NodeEncoder(nn.Module):   # node_encoder.py:79-126
+    def __init__(self, in_dim, h, out_dim, n_layers):
+        super().__init__()
+        self.input_proj = nn.Linear(in_dim, h)
+        self.layers = nn.ModuleList([_Block(h) for _ in range(n_layers)])
+        self.output_proj = nn.Linear(h, out_dim)
+
+
+class _TourEncoder(nn.Module):   # tour_encoder.py:101-157
+    def __init__(self, in_dim, h, out_dim, node_emb_dim, n_layers):
+        super().__init__()
+        self.input_proj = nn.Linear(in_dim, h)
+        self.node_emb_input_proj = nn.Linear(node_emb_dim, h)
+        self.tour_layers = nn.ModuleList([_Block(h) for _ in range(n_layers)])
+        self.rev_tour_layers = nn.ModuleList([_Block(h) for _ in range(n_layers)])
+        self.output_proj = nn.Linear(2 * h, out_dim)
+        self.node_emb_output_proj = nn.Linear(h, out_dim)
+
+
+class _Decoder(nn.Module):       # attn_decoder.py:49-54
+    def __init__(self, q_dim, a_dim, h):
+        super().__init__()
+        self.ctxt_proj = nn.Linear(q_dim, h, bias=False)
+        self.set_proj = nn.Linear(a_dim, 3 * h, bias=False)
+        self.out_proj = nn.Linear(h, h, bias=False)
+
+
+class Policy(nn.Module):
+    """Drop-in for reference ``lib.model.Policy`` (policy.py:19-240) for the gnn_attn architecture.
+
+    Extra keyword (not in the reference): ``precision`` = ``"fp32"`` (CUDA-core path, the 1e-5 parity anchor)
+    or ``"bf16"`` (tcgen05 tensor-core GEMMs with fp32 accumulation and epilogues)."""
+
+    def __init__(self,
+                 observation_space: Dict,
+                 node_encoder_type: Union[str, nn.Module] = "NodeEncoder",
+                 node_encoder_args: Optional[Dict] = None,
+                 tour_encoder_type: Union[str, nn.Module] = "TourEncoder",
+                 tour_encoder_args: Optional[Dict] = None,
+                 decoder_type: Union[str, nn.Module] = "AttnDecoder",
+                 decoder_args: Optional[Dict] = None,
+                 embedding_dim: int = 256,
+                 device: Union[str, int, torch.device] = "cuda",
+                 precision: str = "fp32",
+                 **kwargs):
+        super().__init__()
+        if (node_encoder_type, tour_encoder_type, decoder_type) != ("NodeEncoder", "TourEncoder", "AttnDecoder"):
+            raise NotImplementedError("the CUDA path implements NodeEncoder / TourEncoder / AttnDecoder only")
+        if embedding_dim != 256:
+            raise NotImplementedError("embedding_dim must be 256 (gnn_attn.yaml:6)")
+        _check_cfg("node_encoder_args", node_encoder_args, GNN_ATTN_POLICY_CFG["node_encoder_args"])
+        _check_cfg("tour_encoder_args", tour_encoder_args, GNN_ATTN_POLICY_CFG["tour_encoder_args"])
+        _check_cfg("decoder_args", decoder_args, GNN_ATTN_POLICY_CFG["decoder_args"])
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.observation_space = observation_space
+        self.embedding_dim = embedding_dim
+        self.precision = precision
+        self._device = torch.device(device)
+        self.node_feature_dim = observation_space["node_features"]
+        self.tour_feature_dim = observation_space["tour_features"]
+        if (self.node_feature_dim, self.tour_feature_dim) != (7, 5):
+            raise NotImplementedError("observation space must be node_features=7, tour_features=5 (env.py:25-28)")
+        self.node_encoder = _NodeEncoder(7, 128, 256, 3)
+        self.tour_encoder = _TourEncoder(5, 128, 256, 256, 3)    # num_layers 2 + 1 consolidation layer
+        self.decoder = _Decoder(512, 256, 256)
+        self.static_node_emb = None
+        self._static_key = None
+        self._blob = None
+        self._blob_bf16 = None
+        self._blob_key = None
+        self.decode_type = "greedy"
+        self.sampling_seed = 0
+        self.return_logp = False
+        self._lib = _cabi.load_library()
+        self.to(device=self._device)
+
+    @property
+    def device(self):
+        return self._device
+
+    def reset_parameters(self):
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.LayerNorm)):
+                m.reset_parameters()
+        self._blob_key = None
+
+    def reset_static(self):
+        """Forget the node-encoder output (policy.py:162-165)."""
+        self.static_node_emb = None
+        self._static_key = None
+
+    def set_decode_type(self, decode_type: str) -> None:
+        self.decode_type = decode_type
+
+    # ------------------------------------------------------------------ weights -> device blob
+    def _weights(self) -> "_cabi.Weights":
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._blob is None or key != self._blob_key:
+            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            self._blob = pack_f32(sd).to(self._device)
+            self._blob_bf16 = pack_bf16(sd).to(self._device) if self.precision == "bf16" else None
+            self._blob_key = key
+            self._static_key = None
+        w = _cabi.Weights()
+        w.blob = _cabi.ptr(self._blob)
+        w.n_floats = self._blob.numel()
+        w.blob_bf16 = _cabi.ptr(self._blob_bf16)
+        w.n_bf16 = 0 if self._blob_bf16 is None else self._blob_bf16.numel()
+        w.precision = _cabi.PREC_BF16 if self.precision == "bf16" else _cabi.PREC_F32
+        return w
+
+    def _decode_code(self) -> int:
+        if self.decode_type == "greedy":
+            return _cabi.DECODE_GREEDY
+        if self.decode_type == "sampling":
+            return _cabi.DECODE_SAMPLING
+        raise RuntimeError(f"Unknown decoding type <{self.decode_type}> (Forgot to 'set_decode_type()' ?)")
+
+    def encode_static(self, env, recompute: bool = False):
+        """NodeEncoder.forward once per loaded batch (policy.py:134-135)."""
+        w = self._weights()
+        key = (id(env), env._static_version)
+        if recompute or self.static_node_emb is None or self._static_key != key:
+            _cabi.check(self._lib.jampr_node_encoder(env._dims, env._inst, w, env._stream()), "jampr_node_encoder")
+            self.static_node_emb = env._static_emb
+            self._static_key = key
+        return w
+
+    # ------------------------------------------------------------------ forward (policy.py:120-138)
+    def forward(self, obs: RPObs, recompute_static: bool = False,
+                uniforms: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Optional[Tensor]]:
+        env = getattr(obs, "state", None)
+        if env is None:
+            raise RuntimeError("this Policy consumes observations of jampr_plus_b200.RPEnv (obs.state is missing); "
+                               "there is no PyTorch fallback path")
+        st = env.state
+        st.ensure_policy_buffers(self.return_logp)
+        w = self.encode_static(env, recompute_static)
+        code = self._decode_code()
+        u = None if uniforms is None else uniforms.to(self._device, torch.float32).contiguous()
+        _cabi.check(self._lib.jampr_policy_step(env._dims, env._inst, w, st.struct(), int(env._graph_fresh),
+                                                int(env._step), code, int(self.sampling_seed), _cabi.ptr(u),
+                                                env._stream()), "jampr_policy_step")
+        action = st["action"].long()
+        ll = st["ll"].clone().unsqueeze(-1)
+        ent = None
+        if code == _cabi.DECODE_SAMPLING:
+            # the reference's ActionDist.entropy sums over the whole batch (policy.py:247-252)
+            ent = st["entropy"].sum()
+        return action, ll, ent
+
+    def log_probs(self, env) -> Tensor:
+        """(bs, K*k) log-probabilities of the last forward (needs ``return_logp = True``)."""
+        return env.state["logp"]

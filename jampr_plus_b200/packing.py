@@ -70,3 +70,8 @@ def pack_f32(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     put("LK_W", sp[512:768])
     put("OUT_WT", sd["decoder.out_proj.weight"].t())
     return blob
+
+
+def pack_bf16(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """bf16 GEMM operands for the tensor-core path (layout owned by csrc/encoder_tc.cu)."""
+    raise NotImplementedError("bf16 tensor-core path not built yet")

@@ -1,1 +1,2 @@
 from .formats import RPInstance, RPObs  # noqa: F401
+from .env import RPEnv  # noqa: F401

@@ -1,0 +1,628 @@
+"""Batched CVRP-TW construction environment on the B200: host-side mirror of the reference ``RPEnv``.
+
+Same constructor, ``load_data / reset / step / import_sol / export_sol`` surface and attribute names as
+reference ``lib/routing/env.py:19-1297``; every state transition, candidate set and feasibility mask is
+computed by libjampr_b200.so (include/jampr_b200.h) on ``device``.  There is no CPU implementation here:
+a non-CUDA device raises.
+
+Differences a caller can observe (all documented in INTEGRATION.md):
+  * static data lives once per *instance* on the device (the reference replicates it per sample,
+    env.py:1189-1202); ``coords``/``demands``/``tw`` therefore have leading dimension ``n_inst``.
+  * the observation tuple keeps the reference fields, but the edge lists (``node_nbh_edges`` etc.) are only
+    materialised when ``RPEnv(..., debug>=1)``; the policy reads the device state through ``obs.state``.
+  * data-dependent errors are raised from per-rollout status words after the step (same exception types
+    and messages as the reference: env.py:230-236, :254-258, :1020-1021).
+"""
+import math
+import warnings
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from .formats import RPInstance, RPObs
+
+__all__ = ["RPEnv", "DeviceState"]
+
+_STATE_SPEC = {
+    # name: (dtype, shape as a lambda of dims)
+    "visited": (torch.uint8, lambda s: (s.bs, s.N)),
+    "pred": (torch.int16, lambda s: (s.bs, s.N)),
+    "succ": (torch.int16, lambda s: (s.bs, s.N)),
+    "plan": (torch.int16, lambda s: (s.bs, s.K_max, s.L)),
+    "vflags": (torch.uint8, lambda s: (s.bs, s.K_max)),
+    "row": (torch.int32, lambda s: (s.bs, s.K)),
+    "nxt": (torch.int32, lambda s: (s.bs, s.K)),
+    "cur": (torch.int32, lambda s: (s.bs, s.K)),
+    "row_last": (torch.int32, lambda s: (s.bs, s.K)),
+    "cap": (torch.float32, lambda s: (s.bs, s.K)),
+    "time": (torch.float32, lambda s: (s.bs, s.K)),
+    "cttd": (torch.float32, lambda s: (s.bs, s.K)),
+    "total": (torch.float32, lambda s: (s.bs,)),
+    "cost": (torch.float32, lambda s: (s.bs,)),
+    "status": (torch.int32, lambda s: (s.bs,)),
+    "allvis": (torch.uint8, lambda s: (s.bs,)),
+    "nvis": (torch.int32, lambda s: (s.bs,)),
+    "nbh": (torch.int16, lambda s: (s.bs, s.K, s.k)),
+    "mask": (torch.uint8, lambda s: (s.bs, s.K, s.k)),
+    "action": (torch.int32, lambda s: (s.bs, 2)),
+    "ll": (torch.float32, lambda s: (s.bs,)),
+    "entropy": (torch.float32, lambda s: (s.bs,)),
+    "ctl": (torch.int32, lambda s: (_cabi.CTL_WORDS,)),
+}
+# policy-side buffers, allocated on first use by the policy (they dominate memory: ~1.5 KB * N per rollout)
+_POLICY_SPEC = {
+    "logp": (torch.float32, lambda s: (s.bs, s.K * s.k)),
+    "h_fin": (torch.float32, lambda s: (s.bs, s.N, 128)),
+    "ne": (torch.float32, lambda s: (s.bs, s.N, 256)),
+    "ne_stats": (torch.float32, lambda s: (s.bs, 2, 256)),
+}
+
+
+class DeviceState:
+    """Per-rollout episode state in HBM (struct-of-arrays, layout of jampr_state_t)."""
+
+    def __init__(self, bs: int, N: int, K: int, k: int, K_max: int, L: int, device: torch.device):
+        self.bs, self.N, self.K, self.k, self.K_max, self.L = bs, N, K, k, K_max, L
+        self.device = device
+        self.t = {}
+        for name, (dt, shp) in _STATE_SPEC.items():
+            self.t[name] = torch.zeros(shp(self), dtype=dt, device=device)
+        self.want_logp = False
+        self._struct = None
+
+    def ensure_policy_buffers(self, want_logp: bool = False):
+        changed = False
+        for name, (dt, shp) in _POLICY_SPEC.items():
+            if name == "logp" and not (want_logp or self.want_logp):
+                continue
+            if name not in self.t:
+                self.t[name] = torch.zeros(shp(self), dtype=dt, device=self.device)
+                changed = True
+        self.want_logp = self.want_logp or want_logp
+        if changed:
+            self._struct = None
+
+    def struct(self) -> "_cabi.State":
+        if self._struct is None:
+            s = _cabi.State()
+            for name in _cabi.STATE_FIELDS:
+                setattr(s, name, _cabi.ptr(self.t.get(name)))
+            self._struct = s
+        return self._struct
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        return self.t[name]
+
+
+class RPEnv:
+    """Drop-in for reference ``lib.routing.RPEnv`` (env.py:19-1297) backed by libjampr_b200.so."""
+    OBSERVATION_SPACE = {
+        "node_features": 7,
+        "tour_features": 5,
+    }
+
+    def __init__(self,
+                 check_feasibility: bool = False,
+                 max_concurrent_vehicles: int = 3,
+                 k_nbh_frac: float = 0.25,
+                 pomo: bool = False,
+                 pomo_nbh_frac: float = 0.25,
+                 pomo_single_start_node: bool = False,
+                 num_samples: int = 1,
+                 enable_render: bool = False,
+                 plot_save_dir: Optional[str] = None,
+                 device: Union[torch.device, str] = "cuda",
+                 fp_precision: torch.dtype = torch.float,
+                 inference: bool = False,
+                 tour_graph_update_step: int = 1,
+                 debug: Union[bool, int] = False,
+                 ):
+        self.check_feasibility = check_feasibility
+        self.max_concurrent_vehicles = max_concurrent_vehicles
+        self.k_nbh_frac = k_nbh_frac
+        self.pomo = pomo
+        if self.pomo:
+            if num_samples <= 1:
+                warnings.warn("POMO should use num_samples > 1")
+            self._num_samples = num_samples
+        elif inference:
+            self._num_samples = num_samples
+        else:
+            self._num_samples = 1
+        self.pomo_nbh_frac = pomo_nbh_frac
+        self.pomo_single_start_node = pomo_single_start_node
+        if enable_render:
+            raise NotImplementedError("rendering is outside the accelerated path (reference visualization.py)")
+        self.enable_render = False
+        self.plot_save_dir = plot_save_dir
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("jampr_plus_b200.RPEnv runs on a CUDA device only (no CPU fallback)")
+        if fp_precision != torch.float:
+            raise NotImplementedError("the CUDA environment computes in fp32 (reference default, env.py:41)")
+        self.fp_precision = fp_precision
+        assert tour_graph_update_step != 0
+        self.tour_graph_update_step = tour_graph_update_step
+        # the reference keeps the dense distance matrix only in inference mode (env.py:369-372); the kernels
+        # always use it, which yields the same values (same formula, challenge_utils.py:35)
+        self.inference = inference
+        self.debug_lvl = 2 if isinstance(debug, bool) and debug else int(debug)
+        if self.debug_lvl > 0:
+            self.check_feasibility = True
+        self._lib = _cabi.load_library()
+        self._gen = torch.Generator(device=self.device)
+        self.clear_cache()
+
+    # ------------------------------------------------------------------ plumbing
+    def seed(self, seed: int) -> List[int]:
+        """Reference seeds the global torch RNG (env.py:142-144); the start-node draw here uses a
+        device generator owned by the env, seeded the same way."""
+        torch.manual_seed(seed)
+        self._gen.manual_seed(seed)
+        return [seed]
+
+    def clear_cache(self):
+        self.bs = None
+        self.n_inst = None
+        self.coords = self.demands = self.tw = self.service_time = None
+        self.graph_size = None
+        self.org_service_horizon = None
+        self.max_vehicle_number = None
+        self.vehicle_capacity = None
+        self.service_horizon = None
+        self.time_to_depot = None
+        self._dist_mat = None
+        self.k_nbh_size = None
+        self.ordered_idx = None
+        self._knn = self._knn_w = None
+        self._static_emb = self._h0 = None
+        self._inst_status = None
+        self._dims = None
+        self._inst = None
+        self.state = None
+        self._has_instance = False
+        self._is_reset = False
+        self._step = None
+        self._graph_fresh = True
+        self._static_version = getattr(self, '_static_version', 0) + 1
+        self._table_key = None
+
+    def _stream(self):
+        return _cabi.stream_ptr(self.device)
+
+    # ------------------------------------------------------------------ load_data (env.py:344-418)
+    def load_data(self, batch: List[RPInstance], dist_mat: Optional[torch.Tensor] = None) -> None:
+        """Load a list of RPInstances: uploads them and builds the per-instance tables on the device.
+        ``dist_mat`` (n_inst, N, N), optional and not in the reference: a normalised transit matrix to use
+        instead of evaluating the DIMACS formula on the device."""
+        gs = int(batch[0].graph_size)
+        assert np.all(np.array([x.graph_size for x in batch]) == gs)
+        kv = batch[0].max_vehicle_number
+        assert np.all(np.array([x.max_vehicle_number for x in batch]) == kv)
+        assert np.all(np.array([x.vehicle_capacity for x in batch]) == 1)
+        assert np.all(np.array([x.service_horizon for x in batch]) == 1)
+        assert np.all(np.array([x.depot_idx[0] for x in batch]) == 0)
+        self.vehicle_capacity = batch[0].vehicle_capacity
+        self.service_horizon = batch[0].service_horizon
+        stack = lambda key: torch.from_numpy(np.stack([np.asarray(x[key]) for x in batch])).to(torch.float32)
+        self.load_arrays({"coords": stack("coords"), "demands": stack("demands"), "tw": stack("tw"),
+                          "service_time": stack("service_time"),
+                          "org_service_horizon": stack("org_service_horizon")}, int(kv), dist_mat=dist_mat)
+
+    def load_arrays(self, arrays: dict, max_vehicle_number: int, check: bool = True,
+                    dist_mat: Optional[torch.Tensor] = None) -> None:
+        """Same as load_data for instances that are already stacked: fp32 tensors ``coords (I,N,2)``,
+        ``demands (I,N)``, ``tw (I,N,2)``, ``service_time (I,)``, ``org_service_horizon (I,)`` on the host
+        (pinned memory is copied asynchronously) or on the device.  The tensors are copied, never aliased:
+        the window fix-up (env.py:395-409) modifies ``tw`` in place.  ``check=False`` skips the one
+        device->host read that turns a collapsed window into the reference's AssertionError."""
+        dev = self.device
+        up = lambda t: t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous().clone() \
+            if t.device == dev else t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        self.coords = up(arrays["coords"])
+        self.demands = up(arrays["demands"])
+        self.tw = up(arrays["tw"])
+        self.service_time = up(arrays["service_time"])
+        self.org_service_horizon = up(arrays["org_service_horizon"])
+        I, gs = int(self.coords.size(0)), int(self.coords.size(1))
+        kv = int(max_vehicle_number)
+        self.n_inst = I
+        self.graph_size = gs
+        self.max_vehicle_number = int(kv + np.floor(np.log(kv)))     # env.py:362
+        if self.vehicle_capacity is None:
+            self.vehicle_capacity, self.service_horizon = 1.0, 1.0
+        self.k_nbh_size = math.ceil(self.k_nbh_frac * gs)     # graph_utils.py:99
+        K = self.max_concurrent_vehicles
+        if self.max_vehicle_number > 32767 or gs > 32767:
+            raise ValueError("graph too large for the int16 index tables")
+        N, k = gs, self.k_nbh_size
+        shape_key = (I, N, k)
+        if getattr(self, "_table_key", None) != shape_key:
+            self._dist_mat = torch.empty(I, N, N, dtype=torch.float32, device=dev)
+            self.time_to_depot = torch.empty(I, N, dtype=torch.float32, device=dev)
+            self._knn = torch.empty(I, N, k, dtype=torch.int16, device=dev)
+            self._knn_w = torch.empty(I, N, k, dtype=torch.float32, device=dev)
+            self.ordered_idx = torch.empty(I, N, dtype=torch.int16, device=dev)
+            self._inst_status = torch.zeros(I, dtype=torch.int32, device=dev)
+            self._static_emb = torch.empty(I, N, 256, dtype=torch.float32, device=dev)
+            self._h0 = torch.empty(I, N, 128, dtype=torch.float32, device=dev)
+            self._table_key = shape_key
+        self.bs = I * self._num_samples
+        self._dims = _cabi.Dims(I, self._num_samples, N, K, k, self.max_vehicle_number, min(64, N),
+                                self.tour_graph_update_step)
+        p = _cabi.Instances()
+        for name, t in (("coords", self.coords), ("demand", self.demands), ("tw", self.tw),
+                        ("service", self.service_time), ("horizon", self.org_service_horizon),
+                        ("dist", self._dist_mat), ("ttd", self.time_to_depot), ("knn", self._knn),
+                        ("knn_w", self._knn_w), ("order", self.ordered_idx), ("inst_status", self._inst_status),
+                        ("static_emb", self._static_emb), ("h0", self._h0)):
+            setattr(p, name, _cabi.ptr(t))
+        given = None
+        if dist_mat is not None:
+            given = dist_mat.to(device=dev, dtype=torch.float32).contiguous()
+            assert tuple(given.shape) == (I, N, N)
+        p.dist_given = _cabi.ptr(given)
+        self._inst = p
+        tw_in = None if self.inference else self.tw.clone()
+        _cabi.check(self._lib.jampr_setup_instances(self._dims, self._inst, self._stream()), "jampr_setup_instances")
+        p.dist_given = None           # consumed by the kernel enqueued above (same stream keeps `given` alive)
+        self._dist_given_keepalive = given
+        if tw_in is not None:
+            self.tw.copy_(tw_in)      # the window fix-up is an inference-only step in the reference (env.py:395)
+        if self.inference and check:
+            # reference asserts on the shrunk windows (env.py:408)
+            if bool((self._inst_status & _cabi.ST_TW_COLLAPSE).any().item()):
+                raise AssertionError("time window fix for the return to the depot collapses a window (env.py:408)")
+        self._static_version += 1
+        self._has_instance = True
+        self._is_reset = False
+
+    # ------------------------------------------------------------------ reset (env.py:146-201, 1221-1297)
+    def _pomo_start_nodes(self) -> torch.Tensor:
+        """Start nodes of the POMO pseudo-steps (env.py:1221-1270): the depot neighbourhood without the
+        depot, reduced to the earliest window starts, K distinct uniform picks per rollout; or the
+        deterministic single start node per sample."""
+        I, P, K, k = self.n_inst, self._num_samples, self.max_concurrent_vehicles, self.k_nbh_size
+        nb = self.ordered_idx[:, 1:k].long()
+        tws = self.tw[:, :, 0].gather(1, nb)
+        srt = torch.sort(tws, dim=-1, stable=True).indices
+        if self.pomo_single_start_node:
+            if P > k - 1:
+                raise RuntimeError(f"sample set for POMO has size {k - 1} which is too small for {P} samples!")
+            return nb.gather(1, srt[:, :P]).reshape(-1, 1).to(torch.int32).contiguous()
+        kk = math.floor((k - 1) * self.pomo_nbh_frac)
+        if kk < K:
+            raise RuntimeError(f"sample set for POMO has size {kk} which is too small for {P} samples! "
+                               f"Try increasing 'k_nbh_frac' of env.")
+        cand = nb.gather(1, srt[:, :kk])
+        pick = torch.multinomial(torch.ones(self.bs, kk, device=self.device), K, replacement=False,
+                                 generator=self._gen)
+        cand = cand.repeat_interleave(P, dim=0)
+        return cand.gather(1, pick).to(torch.int32).contiguous()
+
+    def reset(self, start_nodes: Optional[torch.Tensor] = None) -> RPObs:
+        """Reset the simulator and return the initial observation.  ``start_nodes`` (bs, n_start) overrides
+        the random POMO draw (used to replay a recorded episode)."""
+        assert self._has_instance, "need to load instance first."
+        d = self._dims
+        if (self.state is None or self.state.bs != self.bs or self.state.N != d.n_nodes or self.state.k != d.k_nbh
+                or self.state.K_max != d.k_max):
+            self.state = DeviceState(self.bs, d.n_nodes, d.n_slots, d.k_nbh, d.k_max, d.plan_len, self.device)
+        self._step = 0
+        n_start = 0
+        sn = None
+        if self.pomo:
+            sn = self._pomo_start_nodes() if start_nodes is None else \
+                start_nodes.to(self.device, torch.int32).reshape(self.bs, -1).contiguous()
+            n_start = sn.size(1)
+        _cabi.check(self._lib.jampr_env_reset(d, self._inst, self.state.struct(), _cabi.ptr(sn), n_start,
+                                              self._stream()), "jampr_env_reset")
+        self._start_nodes = sn
+        self._step += n_start
+        self._graph_fresh = True
+        self._is_reset = True
+        self._done = False
+        return self._get_observation()
+
+    # ------------------------------------------------------------------ step (env.py:203-311)
+    def step(self, action: torch.Tensor):
+        """One environment step.  Returns (obs | None, cost (bs,), done, info) like the reference."""
+        assert self._is_reset
+        assert action.size(0) == self.bs and action.size(1) == 2
+        st = self.state
+        act = action.to(device=self.device, dtype=torch.int32).contiguous()
+        _cabi.check(self._lib.jampr_env_step(self._dims, self._inst, st.struct(), _cabi.ptr(act), self._step,
+                                             self._stream()), "jampr_env_step")
+        # the reference returns `done` as a Python bool: one device->host read per step (env.py:281);
+        # the fused rollout (jampr_rollout) has no such read
+        done = int(st["ctl"][_cabi.CTL_DONE_STEP].item()) >= 0
+        self._raise_status()
+        self._graph_fresh = (self._step <= self.max_concurrent_vehicles + 1) or \
+                            (self._step % self.tour_graph_update_step == 0)      # env.py:801
+        cost = st["cost"].clone()
+        info = {
+            "current_total_cost": st["total"].cpu().numpy(),
+            "k_used": self.k_used.cpu().numpy() if done else [-1],
+            "max_tour_len": int((st["plan"] == 0).to(torch.uint8).argmax(dim=-1).max().item()),
+        }
+        self._step += 1
+        if done:
+            self._has_instance = False
+            self._is_reset = False
+            self._done = True
+        return (self._get_observation() if not done else None), cost, done, info
+
+    def _raise_status(self, allow_warn: bool = True):
+        """Turn the per-rollout status words into the reference's exceptions / warnings."""
+        status = self.state["status"]
+        if int(status.max().item()) == 0:
+            return
+        has = lambda bit: bool(((status & bit) != 0).any().item())
+        if has(_cabi.ST_TOUR_OVERFLOW):
+            n_inf = int(((status & _cabi.ST_TOUR_OVERFLOW) != 0).sum().item())
+            raise RuntimeError(f"Current rollout could not solve at least {n_inf} instances.")
+        if has(_cabi.ST_NO_FEASIBLE):
+            raise RuntimeError("no feasible nodes left: %s" %
+                               ((status & _cabi.ST_NO_FEASIBLE) != 0).nonzero().view(-1).tolist()[:8])
+        if has(_cabi.ST_NAN_LOGITS):
+            raise AssertionError("Logits contain NANs!")
+        if allow_warn and has(_cabi.ST_FLEET_EXHAUSTED):
+            warnings.warn("used all available vehicles!", RuntimeWarning)
+
+    # ------------------------------------------------------------------ observation (env.py:1042-1073)
+    def _get_observation(self) -> RPObs:
+        st = self.state
+        full = self.debug_lvl > 0
+        node_features = tour_plan = tour_features = None
+        if full:
+            node_features = self.node_features()
+            tour_plan = st["plan"].gather(1, st["row"].long()[:, :, None].expand(self.bs, st.K, st.L)).long()
+            tour_features = self.tour_features()
+        return RPObs(
+            batch_size=self.bs,
+            node_features=node_features,
+            node_nbh_edges=None,
+            node_nbh_weights=None,
+            tour_plan=tour_plan,
+            tour_features=tour_features,
+            tour_edges=None,
+            tour_weights=None,
+            nbh=st["nbh"],
+            nbh_mask=st["mask"].view(torch.bool) if st["mask"].dtype == torch.uint8 else st["mask"],
+            state=self,
+        )
+
+    def node_features(self) -> torch.Tensor:
+        """(n_inst, N, 7): coords, demand, tw, service time, time to depot (env.py:1047-1053)."""
+        I, N = self.n_inst, self.graph_size
+        return torch.cat((self.coords, self.demands[:, :, None], self.tw,
+                          self.service_time[:, None, None].expand(I, N, 1), self.time_to_depot[:, :, None]), -1)
+
+    def tour_features(self) -> torch.Tensor:
+        """(bs, K, 5) as env.py:1061-1068."""
+        st = self.state
+        km = float(self.max_vehicle_number)
+        return torch.stack((st["cur"].float(), st["cap"], st["time"], st["cttd"],
+                            (km - st["row"].float()) / km), -1)
+
+    # ------------------------------------------------------------------ properties (env.py:734-767)
+    @property
+    def num_samples(self):
+        return self._num_samples
+
+    @property
+    def depot_node(self) -> torch.Tensor:
+        return torch.zeros(self.bs, dtype=torch.long, device=self.device)
+
+    @property
+    def visited(self) -> torch.Tensor:
+        return self.state["visited"][:, 1:].bool()
+
+    @property
+    def _visited(self) -> torch.Tensor:
+        return self.state["visited"].bool()
+
+    @property
+    def tour_plan(self) -> torch.Tensor:
+        return self.state["plan"]
+
+    @property
+    def _finished(self) -> torch.Tensor:
+        return (self.state["vflags"] & 2) != 0
+
+    @property
+    def active_vehicles(self) -> torch.Tensor:
+        return (self.state["vflags"] & 1) != 0
+
+    @property
+    def active_to_plan_idx(self) -> torch.Tensor:
+        return self.state["row"].long()
+
+    @property
+    def cur_node(self) -> torch.Tensor:
+        return self.state["cur"].long()
+
+    @property
+    def k_used(self) -> torch.Tensor:
+        """Number of vehicles used per rollout (env.py:754-759)."""
+        st = self.state
+        used = self._finished.clone()
+        en_route = st["cur"] != 0
+        rows = st["row"].long()
+        used.scatter_(1, rows, used.gather(1, rows) | en_route)
+        return used.sum(-1)
+
+    @property
+    def total_cost(self) -> torch.Tensor:
+        return self.state["total"].clone()
+
+    def true_cost(self) -> torch.Tensor:
+        """Batch-independent cost recomputed from the tour buffers."""
+        out = torch.empty(self.bs, dtype=torch.float32, device=self.device)
+        _cabi.check(self._lib.jampr_true_cost(self._dims, self._inst, self.state.struct(), _cabi.ptr(out),
+                                              self._stream()), "jampr_true_cost")
+        return out
+
+    def gather_best(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Best-of-samples per instance (training.py:80-94): (cost (I,), sample idx (I,), tours (I,K_max,L))."""
+        d = self._dims
+        cost = torch.empty(d.n_inst, dtype=torch.float32, device=self.device)
+        idx = torch.empty(d.n_inst, dtype=torch.int32, device=self.device)
+        plan = torch.empty(d.n_inst, d.k_max, d.plan_len, dtype=torch.int16, device=self.device)
+        _cabi.check(self._lib.jampr_gather_best(d, self.state.struct(), _cabi.ptr(cost), _cabi.ptr(idx),
+                                                _cabi.ptr(plan), self._stream()), "jampr_gather_best")
+        return cost, idx, plan
+
+    # ------------------------------------------------------------------ solution I/O (env.py:465-718)
+    def export_sol(self, num_best: int = 3, num_other: int = 3, mode: str = "random"):
+        """Export tour plans as nested lists (env.py:465-573).  ``mode='similarity'`` (difflib, host-side
+        string matching, seq_match.py) is outside the accelerated path."""
+        P = self._num_samples
+        st = self.state
+        plan = st["plan"].view(-1, P, st.K_max, st.L)
+        total = st["total"].view(-1, P)
+        if P > 1:
+            n_smp = num_best + num_other
+            assert P > n_smp, (f"specified selection of total of {n_smp} samples but env was configured "
+                               f"with num_samples = {P} < {n_smp}!")
+            cost_idx = total.sort(dim=-1, stable=True).indices
+            idx = cost_idx[:, :num_best]
+            if mode != "random":
+                raise NotImplementedError(f"selection mode {mode!r} is host-side string matching in the reference "
+                                          f"(seq_match.py) and not part of the accelerated path")
+            if num_other > 0:
+                w = torch.ones(plan.size(0), P - num_best, device=self.device)
+                rnd = torch.multinomial(w, num_other, replacement=False, generator=self._gen)
+                idx = torch.cat((idx, cost_idx[:, num_best:].gather(-1, rnd)), -1)
+            tp = plan.gather(1, idx[:, :, None, None].expand(-1, -1, st.K_max, st.L))
+            return self._sol_to_list(tp), total.gather(-1, idx).cpu().tolist()
+        return self._sol_to_list(plan), st["total"].cpu().tolist()
+
+    def _sol_to_list(self, tp: torch.Tensor):
+        tp = tp.cpu().numpy()
+        full = set(range(self.graph_size))
+        tours = []
+        for plans in tp:
+            tour_set = []
+            for plan in plans:
+                unq = set(np.unique(plan).tolist()) | {0}
+                singles = [[e] for e in sorted(full - unq)]
+                rows = plan[plan.sum(-1) > 0]
+                tour_set.append([r[r > 0].tolist() for r in rows] + singles)
+            tours.append(tour_set)
+        return tours
+
+    def import_sol(self, sol: List[List], cost: Optional[List] = None) -> RPObs:
+        """Import partial solutions (env.py:575-706).  The list parsing stays on the host like the
+        reference's; state arrays are assembled in numpy, uploaded once, and the device derives visited
+        flags / tour links / the first observation (jampr_env_import_finish)."""
+        assert self.inference, "Can only import solutions in inference mode."
+        assert self.state is not None, "import_sol needs a previous reset() (reference reuses its buffers)"
+        P = self._num_samples
+        I = self.n_inst
+        assert len(sol) == I
+        n_samples = np.array([len(s) for s in sol])
+        assert np.all(n_samples == n_samples[0])
+        n_samples = int(n_samples[0])
+        if self.pomo:
+            assert P == n_samples, (f"imported solutions for POMO must include num_samples samples, "
+                                    f"but got {n_samples} != {P}")
+        else:
+            assert P % n_samples == 0
+        fact = P // n_samples
+        st = self.state
+        bs, K, K_max, L = self.bs, st.K, st.K_max, st.L
+        plan = np.zeros((bs, K_max, L), dtype=np.int16)
+        vfl = np.zeros((bs, K_max), dtype=np.uint8)
+        row = np.zeros((bs, K), dtype=np.int32)
+        nxt = np.zeros((bs, K), dtype=np.int32)
+        cur = np.zeros((bs, K), dtype=np.int32)
+        cap = np.ones((bs, K), dtype=np.float32)
+        tim = np.zeros((bs, K), dtype=np.float32)
+        cttd = np.zeros((bs, K), dtype=np.float32)
+        total = np.zeros(bs, dtype=np.float32)
+        dist = self._dist_mat.cpu().numpy()
+        tw0 = self.tw[:, :, 0].cpu().numpy()
+        dem = self.demands.cpu().numpy()
+        ttd = self.time_to_depot.cpu().numpy()
+        srv = self.service_time.cpu().numpy()
+
+        def recompute(tour, i):      # env.py:708-718, fp32 accumulation like the reference tensors
+            tm = np.float32(0.0)
+            prev = 0
+            for n in tour:
+                tm = np.float32(tm + dist[i, prev, n])
+                tm = np.float32(tm + np.float32(np.maximum(np.float32(tw0[i, n] - tm), np.float32(0)) + srv[i]))
+                prev = n
+            return float(tm)
+
+        b = 0
+        for i, inst_sol in enumerate(sol):
+            for smp in inst_sol:
+                num_partial = 0
+                t_idx = 0
+                costs = []
+                for tour in smp:
+                    l = len(tour)
+                    if l <= 1:
+                        continue
+                    if t_idx >= K_max:
+                        raise RuntimeError("Number of tours of provided solution is larger than max_num_vehicles!")
+                    if tour[0] == tour[-1] == 0:
+                        plan[b, t_idx, :l - 1] = np.asarray(tour[1:], dtype=np.int16)
+                        vfl[b, t_idx] |= 2
+                        costs.append(recompute(tour, i))
+                    else:
+                        assert num_partial < K
+                        t = np.asarray(tour, dtype=np.int64)
+                        plan[b, t_idx, :l] = t.astype(np.int16)
+                        cur[b, num_partial] = t[-1]
+                        cap[b, num_partial] = np.float32(1.0) - dem[i, t].sum(dtype=np.float32)
+                        cttd[b, num_partial] = ttd[i, t[-1]]
+                        tm = recompute(tour, i)
+                        costs.append(tm)
+                        tim[b, num_partial] = tm
+                        nxt[b, num_partial] = l
+                        vfl[b, t_idx] |= 1
+                        row[b, num_partial] = t_idx
+                        num_partial += 1
+                    t_idx += 1
+                assert num_partial <= K
+                for s in range(num_partial, K):
+                    free = np.flatnonzero(vfl[b] == 0)
+                    nf = int(free[0]) if free.size else 0
+                    vfl[b, nf] |= 1
+                    row[b, s] = nf
+                # rows were handed out in ascending order, which is what the reference's
+                # active_vehicles.nonzero() re-derivation yields (env.py:697)
+                total[b] = np.float32(sum(costs)) if cost is None else 0.0
+                for r in range(1, fact):      # _expand_sample_dimension (env.py:1204-1219)
+                    for arr in (plan, vfl, row, nxt, cur, cap, tim, cttd, total):
+                        arr[b + r] = arr[b]
+                b += fact
+        if cost is not None:
+            total = np.repeat(np.asarray(cost, dtype=np.float32).reshape(-1), fact)[:bs] \
+                if np.asarray(cost).size != bs else np.asarray(cost, dtype=np.float32).reshape(-1)
+        for name, arr in (("plan", plan), ("vflags", vfl), ("row", row), ("nxt", nxt), ("cur", cur), ("cap", cap),
+                          ("time", tim), ("cttd", cttd), ("total", total)):
+            st[name].copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(self.device))
+        st["row_last"].zero_()
+        st["cost"].zero_()
+        max_step = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _cabi.check(self._lib.jampr_env_import_finish(self._dims, self._inst, st.struct(), _cabi.ptr(max_step),
+                                                      self._stream()), "jampr_env_import_finish")
+        # the reference rebuilds the tour graph with the PREVIOUS episode's step counter (env.py:700 before
+        # :704): same rule, same stale value
+        prev_step = self._step if self._step is not None else 0
+        self._graph_fresh = (prev_step <= K + 1) or (prev_step % self.tour_graph_update_step == 0)
+        self._has_instance = True
+        self._is_reset = True
+        self._done = False
+        self._step = int(max_step.item())
+        self._raise_status()
+        return self._get_observation()
+
+    def destruct(self, **kwargs):
+        raise NotImplementedError

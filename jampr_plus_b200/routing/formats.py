@@ -50,3 +50,4 @@ class RPObs(NamedTuple):
     tour_weights: torch.Tensor        # (E_t,) f32
     nbh: torch.Tensor                 # (bs, K, k) i64
     nbh_mask: torch.Tensor            # (bs, K, k) bool, True = infeasible
+    state: Any = None                 # extension: the env whose device state the policy kernels read

@@ -42,8 +42,9 @@ def start_nodes_of(g: dict):
     return torch.from_numpy(sp[:, :K, 0].astype(np.int64))
 
 
-def make_oracle(g: dict):
+def make_oracle(g: dict, recorded_dist: bool = True):
+    """recorded_dist: replay with the transit matrix the reference itself computed (see dimacs_dist)."""
     env = OracleEnv(**env_args(g["env_kwargs"]))
-    env.load(g["instances"])
+    env.load(g["instances"], dist=torch.from_numpy(g["static_dist"]) if recorded_dist else None)
     pol = OraclePolicy(random_state_dict(int(g["policy_seed"])))
     return env, pol
