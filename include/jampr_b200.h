@@ -120,6 +120,7 @@ typedef struct {
  * Offsets (in floats) are given by jampr_weight_offsets(). */
 #define JAMPR_PREC_F32  0   /* fp32 CUDA-core path: the 1e-5 parity anchor */
 #define JAMPR_PREC_BF16 1   /* bf16 tcgen05 tensor-core GEMMs, fp32 accumulate and epilogues */
+#define JAMPR_PREC_F16  2   /* same tensor-core path with fp16 operands (11-bit significand) */
 
 typedef struct {
   const float* blob;       /* fp32 blob, layout = jampr_weight_offsets() */
@@ -198,6 +199,13 @@ JAMPR_API int jampr_gather_best(const jampr_dims_t* d, const jampr_state_t* st, 
  * return leg, + 2*time_to_depot per unvisited customer (logic of env.py:708-718, 287-295). */
 JAMPR_API int jampr_true_cost(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_state_t* st,
                     float* out, void* stream);
+
+/* Diagnostic: one 128 x N x K tcgen05 tile product D = A * B^T built from the same pieces as the tensor-core
+ * encoder (thread-written swizzled A tile, bulk-copied pre-swizzled B image, TMEM accumulator read-back).
+ * A (128,K) row-major 16-bit, Bimg = packing.sw128_image(B (N,K)), D (128,N) fp32.  precision = JAMPR_PREC_BF16
+ * or JAMPR_PREC_F16.  Replaces nothing in the reference; tests/test_gpu_tc.py pins the UMMA descriptors with it. */
+JAMPR_API int jampr_selftest_umma(const void* A, const void* Bimg, float* D, int32_t K, int32_t N, int32_t precision,
+                                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libjampr_b200.so")
 ABI_VERSION = 1
 ST_NO_FEASIBLE, ST_TOUR_OVERFLOW, ST_FLEET_EXHAUSTED, ST_NAN_LOGITS, ST_TW_COLLAPSE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLING = 0, 1
-PREC_F32, PREC_BF16 = 0, 1
+PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
 CTL_N_ALLVIS, CTL_DONE_STEP, CTL_WORDS = 0, 1, 8
 ERRORS = {-1: "bad argument", -2: "graph too large for the on-chip tile of this build", -3: "unsupported"}
 
@@ -47,7 +47,8 @@ class Weights(C.Structure):
 
 SYMBOLS = ("jampr_abi_version", "jampr_weight_blob_floats", "jampr_weight_offsets", "jampr_setup_instances",
            "jampr_node_encoder", "jampr_env_reset", "jampr_env_step", "jampr_env_import_finish",
-           "jampr_tour_encoder", "jampr_policy_step", "jampr_rollout", "jampr_gather_best", "jampr_true_cost")
+           "jampr_tour_encoder", "jampr_policy_step", "jampr_rollout", "jampr_gather_best", "jampr_true_cost",
+           "jampr_selftest_umma")
 
 _lib = None
 
@@ -75,6 +76,7 @@ def load_library():
     lib.jampr_rollout.argtypes = [PD, PI, PW, PS, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, _p]
     lib.jampr_gather_best.argtypes = [PD, PS, _p, _p, _p, _p]
     lib.jampr_true_cost.argtypes = [PD, PI, PS, _p, _p]
+    lib.jampr_selftest_umma.argtypes = [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("jampr_weight_blob_floats",):

@@ -72,6 +72,23 @@ def pack_f32(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     return blob
 
 
+def sw128_image(w: torch.Tensor) -> torch.Tensor:
+    """Shared-memory image of a K-major UMMA operand with the 128-byte swizzle (csrc/tc_ptx.cuh).
+
+    ``w`` is (rows, K) of a 16-bit dtype, K a multiple of 64.  The image is K/64 tiles of [rows][64 elements]
+    (128 B per row); inside a tile the 16-byte chunk c of row r sits at chunk position c ^ (r & 7).  A bulk
+    copy of the image into 1024-byte aligned shared memory is directly consumable by tcgen05.mma."""
+    assert w.dim() == 2 and w.element_size() == 2 and w.size(1) % 64 == 0
+    rows, K = w.shape
+    nkb = K // 64
+    t = w.contiguous().view(torch.int16).view(rows, nkb, 8, 8)            # (r, kb, chunk, 8 elements)
+    r = torch.arange(rows).view(rows, 1, 1).expand(rows, nkb, 8)
+    c = torch.arange(8).view(1, 1, 8).expand(rows, nkb, 8)
+    src = (c ^ (r & 7))                                                   # position p holds chunk p ^ (r & 7)
+    img = torch.gather(t, 2, src.unsqueeze(-1).expand(rows, nkb, 8, 8))
+    return img.permute(1, 0, 2, 3).contiguous().view(-1).view(w.dtype)
+
+
 def pack_bf16(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     """bf16 GEMM operands for the tensor-core path (layout owned by csrc/encoder_tc.cu)."""
     raise NotImplementedError("bf16 tensor-core path not built yet")

@@ -403,9 +403,10 @@ class RPEnv:
     def tour_features(self) -> torch.Tensor:
         """(bs, K, 5) as env.py:1061-1068."""
         st = self.state
-        km = float(self.max_vehicle_number)
+        num = (self.max_vehicle_number - st["row"]).float()
+        # tensor / tensor: ATen turns division by a host scalar into a multiplication by the reciprocal on CUDA
         return torch.stack((st["cur"].float(), st["cap"], st["time"], st["cttd"],
-                            (km - st["row"].float()) / km), -1)
+                            num / torch.full_like(num, float(self.max_vehicle_number))), -1)
 
     # ------------------------------------------------------------------ properties (env.py:734-767)
     @property
