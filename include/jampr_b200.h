@@ -125,8 +125,8 @@ typedef struct {
 typedef struct {
   const float* blob;       /* fp32 blob, layout = jampr_weight_offsets() */
   int64_t      n_floats;
-  const void*  blob_bf16;  /* bf16 GEMM operands in UMMA tile order (packing.py), or NULL */
-  int64_t      n_bf16;
+  const void*  blob_bf16;  /* 16-bit (bf16 or fp16, see precision) operands in UMMA tile order (packing.pack_tc), or NULL */
+  int64_t      n_bf16;     /* elements of blob_bf16 */
   int32_t      precision;  /* JAMPR_PREC_* */
   int32_t      reserved;
 } jampr_weights_t;
@@ -136,6 +136,8 @@ JAMPR_API int jampr_abi_version(void);
 /* Number of floats of the packed weight blob and the offset table (names in packing.py).
  * Replaces nothing in the reference; it is the checkpoint -> device contract. */
 JAMPR_API int64_t jampr_weight_blob_floats(void);
+/* Number of 16-bit elements of the tensor-core operand blob (packing.pack_tc; layout in csrc/policy_tc.cu). */
+JAMPR_API int64_t jampr_weight_blob16_elems(void);
 JAMPR_API int jampr_weight_offsets(int64_t* out, int32_t max_entries);
 
 /* RPEnv.load_data static part: distance matrix, window fix-up, kNN table, depot order.

@@ -45,7 +45,7 @@ class Weights(C.Structure):
                 ("precision", C.c_int32), ("reserved", C.c_int32)]
 
 
-SYMBOLS = ("jampr_abi_version", "jampr_weight_blob_floats", "jampr_weight_offsets", "jampr_setup_instances",
+SYMBOLS = ("jampr_abi_version", "jampr_weight_blob_floats", "jampr_weight_blob16_elems", "jampr_weight_offsets", "jampr_setup_instances",
            "jampr_node_encoder", "jampr_env_reset", "jampr_env_step", "jampr_env_import_finish",
            "jampr_tour_encoder", "jampr_policy_step", "jampr_rollout", "jampr_gather_best", "jampr_true_cost",
            "jampr_selftest_umma")
@@ -79,9 +79,10 @@ def load_library():
     lib.jampr_selftest_umma.argtypes = [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("jampr_weight_blob_floats",):
+        if name not in ("jampr_weight_blob_floats", "jampr_weight_blob16_elems"):
             fn.restype = C.c_int
     lib.jampr_weight_blob_floats.restype = C.c_int64
+    lib.jampr_weight_blob16_elems.restype = C.c_int64
     if lib.jampr_abi_version() != ABI_VERSION:
         raise ImportError("libjampr_b200.so ABI version mismatch; rebuild")
     _lib = lib
@@ -111,7 +112,7 @@ def weight_offsets() -> dict:
     buf = (C.c_int64 * 32)()
     n = check(lib.jampr_weight_offsets(buf, 32), "jampr_weight_offsets")
     names = ("NE_IN_WT", "NE_IN_B", "NE_BLK", "NE_OUT_WT", "NE_OUT_B", "TE_IN_WT", "TE_IN_B", "TE_BLK", "TE_OUT_WT",
-             "TE_OUT_B", "TF_WT", "TF_B", "TO_WT", "TO_B", "CTXT_WT", "GK_W", "GV_WT", "LK_W", "OUT_WT", "END",
-             "BLK_FLOATS")
+             "TE_OUT_B", "TF_WT", "TF_B", "TO_WT", "TO_B", "CTXT_WT", "GK_W", "GV_WT", "LK_W", "OUT_WT", "TOF_WT",
+             "TOF_B", "END", "BLK_FLOATS")
     assert n == len(names)
     return {k: int(buf[i]) for i, k in enumerate(names)}

@@ -72,5 +72,8 @@ enum {
   OFF_GV_WT = OFF_GK_W + 256 * 256,                 // [256][256] set_proj rows 256..511, transposed
   OFF_LK_W = OFF_GV_WT + 256 * 256,                 // [256][256] set_proj rows 512..767 (as stored)
   OFF_OUT_WT = OFF_LK_W + 256 * 256,                // [256][256] out_proj^T
-  OFF_END = OFF_OUT_WT + 256 * 256
+  OFF_TOF_WT = OFF_OUT_WT + 256 * 256,              // [8][256] (5 rows used) output_proj[:, :128] @ tour input_proj: the
+                                                    // tour-feature branch of tour_encoder.py:202-213 folded (tensor-core path)
+  OFF_TOF_B = OFF_TOF_WT + 8 * 256,                 // [256] output_proj[:, :128] @ input_proj.bias + output_proj.bias
+  OFF_END = OFF_TOF_B + 256
 };

@@ -1,0 +1,877 @@
+// Tensor-core policy step (sm_100a): the per-step tour-graph GNN (tour_encoder.py:159-220), the node-embedding
+// projection (:217-218), the per-tour embeddings (:202-213, :226-243) and the pointer decoder with action
+// selection (policy.py:170-227, attn_decoder.py:62-98) fused into ONE kernel, one CTA per rollout.
+//
+//   * The six GraphConv blocks are [agg | h] (128 x 256) x W_l (256 x 128) products on the 5th-gen tensor cores:
+//     tcgen05.mma (M=128, N=128, K=16 per instruction, 16-bit operands, fp32 accumulation in TMEM) issued by one
+//     thread; A = the CTA's own shared-memory tiles (K-major, 128-byte swizzle) that the aggregation phase and the
+//     previous layer's epilogue write in place; B = pre-swizzled weight tile images streamed from L2 by the bulk
+//     async-copy engine (cp.async.bulk + mbarrier complete_tx) into four 16 KB stages, one layer ahead.
+//   * lin_root(h) (K-blocks 2,3) is issued before the max-aggregation runs, so that half of every layer's tensor
+//     work overlaps the CUDA-core aggregation; lin_rel(agg) (K-blocks 0,1) follows it.
+//   * Epilogue per layer (bias, exact-erf GELU to 1.5e-7, skip, LayerNorm) runs on the accumulator rows read back
+//     with tcgen05.ld; the fp32 skip operand lives in TMEM too (columns 128..255, tcgen05.st), so the only
+//     16-bit roundings on the path are the GEMM operands themselves.
+//   * node_emb = h W_o^T + b + static_emb is a 128 x 256 x 128 product into TMEM columns 0..255; its fp32 rows are
+//     parked in shared memory (over the dead operand tiles) where the decoder reads them: the action embeddings
+//     are never materialised and nothing but the chosen action goes back to HBM (unless the embedding cache is
+//     needed for tour_graph_update_step > 1 or a caller asks for it).
+//   * Decoder algebra: as in decoder.cu the set_proj thirds are moved onto the query side; in addition
+//     out_proj and the logit-key third are pre-multiplied on the host (M1 = W_lk^T W_out) and the tour-feature
+//     branch of tour_encoder.output_proj is folded into a 5 x 256 matrix (packing.py).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace tc;
+
+#define PT_THREADS 512
+#define NE_STRIDE 260                 // fp32 row stride of the parked node embedding (260 % 32 = 4: conflict-free rows)
+#define OVERLAY_BYTES (128 * NE_STRIDE * 4)   // 133120 >= operand tiles (65536) + weight stages (65536)
+#define QP_STRIDE 260
+
+// 16-bit weight blob (elements), mirrors packing.pack_tc
+#define W16_STAGE 8192                                  // one 16 KB stage = [128 rows][64 K] elements
+#define W16_ENC 0                                       // 7 x 4 stages: layers 0..5, then node_emb_output_proj
+#define W16_TO2 (W16_ENC + 28 * W16_STAGE)              // [128][256]  tour output_proj, per-tour-mean half, transposed
+#define W16_CTXT (W16_TO2 + 128 * 256)                  // [512][256]  ctxt_proj^T
+#define W16_GK (W16_CTXT + 512 * 256)                   // [256][256]  set_proj rows 0..255 as stored
+#define W16_GV (W16_GK + 256 * 256)                     // [256][256]  set_proj rows 256..511, transposed
+#define W16_M1 (W16_GV + 256 * 256)                     // [256][256]  (W_lk^T W_out)^T
+#define W16_END (W16_M1 + 256 * 256)
+
+struct PtArgs {
+  jampr_dims_t d;
+  jampr_instances_t p;
+  jampr_state_t st;
+  const float* w;        // fp32 blob (biases, LayerNorm, folded tour-feature matrix)
+  const void* w16;       // 16-bit blob
+  const float* uniforms;
+  uint64_t seed;
+  int step_no;
+  int decode_type;
+  int graph_fresh;
+  int store_cache;       // write h_fin / ne / ne_stats to HBM (needed when later steps reuse them)
+};
+
+template <typename T>
+__device__ __forceinline__ T to_T(float v);
+template <>
+__device__ __forceinline__ __half to_T<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_T<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <typename T>
+__device__ __forceinline__ float from_T(T v);
+template <>
+__device__ __forceinline__ float from_T<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float from_T<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ uint16_t bits_T(float v) {
+  T t = to_T<T>(v);
+  return *reinterpret_cast<uint16_t*>(&t);
+}
+
+// erf to 1.5e-7 absolute (Abramowitz-Stegun 7.1.26) -> GELU(erf) well inside the 16-bit operand noise
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  p *= t;
+  const float e = __expf(-ax * ax);
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(copysignf(erf_abs, x), hx, hx);
+}
+
+// ---- one K-block (64 of K) of a 128 x 128 tile product: 4 tcgen05.mma of K = 16
+__device__ __forceinline__ void mma_kblock(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_f16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_w_stage(uint8_t* sW, int stage, const void* w16, int layer, uint64_t* full) {
+  mbar_arrive_expect_tx(&full[stage], 16384u);
+  bulk_g2s(sW + stage * 16384, reinterpret_cast<const uint8_t*>(w16) + ((size_t)(W16_ENC + (layer * 4 + stage) * W16_STAGE)) * 2,
+           16384u, &full[stage]);
+}
+
+// ---- max aggregation over the static neighbourhood graph into the agg tiles (K-blocks 0,1), packed 16-bit math.
+// tid < 16: the depot row (receives from every node, weight = time to depot); the other 496 threads: 31 customers
+// at a time, 16 threads (16-byte chunks of the 128 features) per customer.
+template <typename T>
+__device__ __forceinline__ void agg_nbh_tc(uint8_t* sA, const uint32_t* s_tab, const T* s_ttd, int N, int k) {
+  using T2 = typename Elem<T>::T2;
+  const int tid = threadIdx.x;
+  const uint8_t* sH = sA + 2 * 16384;
+  if (tid < 16) {
+    const uint32_t kboff = (uint32_t)(tid >> 3) * 16384u, c = tid & 7;
+    T2 m[4];
+    for (int u = 0; u < N; ++u) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sH + kboff + sw128_off(u, c));
+      T2 w2;
+      w2.x = s_ttd[u];
+      w2.y = s_ttd[u];
+      const T2 p0 = __hmul2(from_u32<T2>(v.x), w2), p1 = __hmul2(from_u32<T2>(v.y), w2);
+      const T2 p2 = __hmul2(from_u32<T2>(v.z), w2), p3 = __hmul2(from_u32<T2>(v.w), w2);
+      if (u == 0) { m[0] = p0; m[1] = p1; m[2] = p2; m[3] = p3; }
+      else { m[0] = __hmax2(m[0], p0); m[1] = __hmax2(m[1], p1); m[2] = __hmax2(m[2], p2); m[3] = __hmax2(m[3], p3); }
+    }
+    *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
+  } else {
+    const int g = (tid - 16) >> 4, cc = (tid - 16) & 15;
+    const uint32_t kboff = (uint32_t)(cc >> 3) * 16384u, c = cc & 7;
+    for (int u = 1 + g; u < N; u += 31) {
+      const uint32_t* tb = s_tab + u * k;
+      T2 m[4];
+#pragma unroll 2
+      for (int j = 0; j < k; ++j) {
+        const uint32_t e = tb[j];
+        const uint32_t nb = e & 0xffffu;
+        const T2 w2 = from_u32<T2>(__byte_perm(e, e, 0x3232));
+        const uint4 v = *reinterpret_cast<const uint4*>(sH + kboff + nb * 128u + ((c ^ (nb & 7u)) << 4));
+        const T2 p0 = __hmul2(from_u32<T2>(v.x), w2), p1 = __hmul2(from_u32<T2>(v.y), w2);
+        const T2 p2 = __hmul2(from_u32<T2>(v.z), w2), p3 = __hmul2(from_u32<T2>(v.w), w2);
+        if (j == 0) { m[0] = p0; m[1] = p1; m[2] = p2; m[3] = p3; }
+        else { m[0] = __hmax2(m[0], p0); m[1] = __hmax2(m[1], p1); m[2] = __hmax2(m[2], p2); m[3] = __hmax2(m[3], p3); }
+      }
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, c)) = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
+    }
+  }
+}
+
+// ---- max aggregation over the tour graph (env.py:804-835): customer u receives from link[u] (its predecessor, or
+// successor in the reversed graph) if it is on a tour, nothing otherwise; the depot receives from the tour ends.
+template <typename T>
+__device__ __forceinline__ void agg_tour_tc(uint8_t* sA, const uint8_t* s_vis, const int16_t* s_link, const T* s_wlink,
+                                            const int16_t* s_ends, int n_ends, const T* s_ttd, int N) {
+  using T2 = typename Elem<T>::T2;
+  const int tid = threadIdx.x;
+  const uint8_t* sH = sA + 2 * 16384;
+  if (tid < 16) {
+    const uint32_t kboff = (uint32_t)(tid >> 3) * 16384u, c = tid & 7;
+    T2 m[4];
+    m[0] = m[1] = m[2] = m[3] = Elem<T>::bcast(0.0f);
+    for (int i = 0; i < n_ends; ++i) {
+      const int u = s_ends[i];
+      const uint4 v = *reinterpret_cast<const uint4*>(sH + kboff + sw128_off(u, c));
+      T2 w2;
+      w2.x = s_ttd[u];
+      w2.y = s_ttd[u];
+      const T2 p0 = __hmul2(from_u32<T2>(v.x), w2), p1 = __hmul2(from_u32<T2>(v.y), w2);
+      const T2 p2 = __hmul2(from_u32<T2>(v.z), w2), p3 = __hmul2(from_u32<T2>(v.w), w2);
+      if (i == 0) { m[0] = p0; m[1] = p1; m[2] = p2; m[3] = p3; }
+      else { m[0] = __hmax2(m[0], p0); m[1] = __hmax2(m[1], p1); m[2] = __hmax2(m[2], p2); m[3] = __hmax2(m[3], p3); }
+    }
+    *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
+  } else {
+    const int g = (tid - 16) >> 4, cc = (tid - 16) & 15;
+    const uint32_t kboff = (uint32_t)(cc >> 3) * 16384u, c = cc & 7;
+    for (int u = 1 + g; u < N; u += 31) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (s_vis[u]) {
+        const uint32_t nb = (uint32_t)s_link[u];
+        T2 w2;
+        w2.x = s_wlink[u];
+        w2.y = s_wlink[u];
+        const uint4 v = *reinterpret_cast<const uint4*>(sH + kboff + nb * 128u + ((c ^ (nb & 7u)) << 4));
+        o = make_uint4(as_u32(__hmul2(from_u32<T2>(v.x), w2)), as_u32(__hmul2(from_u32<T2>(v.y), w2)),
+                       as_u32(__hmul2(from_u32<T2>(v.z), w2)), as_u32(__hmul2(from_u32<T2>(v.w), w2)));
+      }
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, c)) = o;
+    }
+  }
+}
+
+// ---- layer epilogue: y = GELU(acc + b) + skip -> LayerNorm -> new h (fp32 into the TMEM skip columns, 16-bit into
+// the h tiles, optionally fp32 to HBM).  Thread (q, lane, cg): row 32q+lane, columns 32cg..32cg+31.
+template <typename T>
+__device__ __forceinline__ void layer_epilogue(uint32_t tmem, uint8_t* sA, float2* s_red, const float* __restrict__ blk,
+                                               int N, float* __restrict__ hfin) {
+  using T2 = typename Elem<T>::T2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cg = warp >> 2, r = q * 32 + lane;
+  const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16);
+  uint32_t acc[32], sk[32];
+  tmem_ld32_nowait(ta + cg * 32, acc);
+  tmem_ld32_nowait(ta + 128 + cg * 32, sk);
+  tmem_wait_ld();
+  float s = 0.0f, qq = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float x = __uint_as_float(acc[j]) + __ldg(blk + BLK_B + cg * 32 + j);
+    const float y = gelu_fast(x) + __uint_as_float(sk[j]);
+    acc[j] = __float_as_uint(y);
+    s += y;
+    qq = fmaf(y, y, qq);
+  }
+  s_red[cg * 128 + r] = make_float2(s, qq);
+  __syncthreads();
+  float ts = 0.0f, tq = 0.0f;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float2 v = s_red[g * 128 + r];
+    ts += v.x;
+    tq += v.y;
+  }
+  const float mean = ts * (1.0f / 128.0f);
+  const float var = fmaxf(fmaf(-mean, mean, tq * (1.0f / 128.0f)), 0.0f);
+  const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = cg * 32 + j;
+    const float o = (__uint_as_float(acc[j]) - mean) * rstd * __ldg(blk + BLK_G + c) + __ldg(blk + BLK_BETA + c);
+    acc[j] = __float_as_uint(o);
+  }
+  tmem_st32(ta + 128 + cg * 32, acc);
+  if (r < N) {
+    uint8_t* tile = sA + (2 + (cg >> 1)) * 16384;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        pk[e] = as_u32(Elem<T>::from2(__uint_as_float(acc[i * 8 + 2 * e]), __uint_as_float(acc[i * 8 + 2 * e + 1])));
+      *reinterpret_cast<uint4*>(tile + sw128_off(r, (cg & 1) * 4 + i)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if (hfin) {
+      float4* dst = reinterpret_cast<float4*>(hfin + (size_t)r * 128 + cg * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                             __uint_as_float(acc[4 * i + 3]));
+    }
+  }
+  tmem_wait_st();
+}
+
+// ---- decoder mat-vec partials: y[o] = sum_c x[c] W[c][o] over 256 outputs, W 16-bit [K][256].  A thread owns OPT
+// adjacent outputs and one of 512*OPT/256 K-slices; partial sums go to s_part[(slice * NV + v) * 256 + o].
+template <typename T, int OPT, int NV>
+__device__ __forceinline__ void matvec_partial(const T* __restrict__ W, int K, const float* x, int xstride, float* s_part) {
+  using T2 = typename Elem<T>::T2;
+  constexpr int NG = 256 / OPT, NS = PT_THREADS / NG;
+  const int og = threadIdx.x % NG, ks = threadIdx.x / NG;
+  const int kn = K / NS, k0 = ks * kn;
+  float acc[NV][OPT];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) acc[v][j] = 0.0f;
+  const T* wp = W + (size_t)k0 * 256 + og * OPT;
+#pragma unroll 4
+  for (int c = 0; c < kn; ++c) {
+    float wv[OPT];
+    if constexpr (OPT == 8) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)c * 256));
+      const float2 f0 = Elem<T>::to2(from_u32<T2>(raw.x)), f1 = Elem<T>::to2(from_u32<T2>(raw.y));
+      const float2 f2 = Elem<T>::to2(from_u32<T2>(raw.z)), f3 = Elem<T>::to2(from_u32<T2>(raw.w));
+      wv[0] = f0.x; wv[1] = f0.y; wv[2] = f1.x; wv[3] = f1.y; wv[4] = f2.x; wv[5] = f2.y; wv[6] = f3.x; wv[7] = f3.y;
+    } else {
+      static_assert(OPT == 2, "OPT must be 8 or 2");
+      const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(wp + (size_t)c * 256));
+      const float2 f0 = Elem<T>::to2(from_u32<T2>(raw));
+      wv[0] = f0.x; wv[1] = f0.y;
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float xv = x[v * xstride + k0 + c];
+#pragma unroll
+      for (int j = 0; j < OPT; ++j) acc[v][j] = fmaf(wv[j], xv, acc[v][j]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) s_part[(ks * NV + v) * 256 + og * OPT + j] = acc[v][j];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtArgs a) {
+  using T2 = typename Elem<T>::T2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const jampr_dims_t& d = a.d;
+  const jampr_state_t& st = a.st;
+  const jampr_instances_t& p = a.p;
+  const int done_step = st.ctl[JAMPR_CTL_DONE_STEP];
+  if (done_step >= 0 && done_step < a.step_no) return;
+  const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh, A = K * k, L = d.plan_len;
+  const int b = blockIdx.x, ins = b / d.n_samples;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* __restrict__ w = a.w;
+  const T* __restrict__ w16 = reinterpret_cast<const T*>(a.w16);
+  const bool fresh = a.graph_fresh != 0;
+
+  // ---------------------------------------------------------------- shared memory carve-up
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = base;               // 4 operand tiles: agg (K-blocks 0,1), h (K-blocks 2,3)
+  uint8_t* sW = base + 65536;       // 4 weight stages
+  float* s_ne = reinterpret_cast<float*>(base);   // node embedding rows, parked over sA/sW once the GNN is done
+  uint8_t* cur = base + OVERLAY_BYTES;
+  auto take = [&](size_t bytes) {
+    uint8_t* r = cur;
+    cur += (bytes + 15) & ~size_t(15);
+    return r;
+  };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(take(64));     // full[0..3], root, acc
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(take(16));
+  float2* s_red = reinterpret_cast<float2*>(take(4 * 128 * sizeof(float2)));
+  float* s_part = reinterpret_cast<float*>(take(16 * 256 * 4));
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(take((size_t)N * k * 4));
+  T* s_ttd = reinterpret_cast<T*>(take(N * 2));
+  T* s_wpred = reinterpret_cast<T*>(take(N * 2));
+  T* s_wsucc = reinterpret_cast<T*>(take(N * 2));
+  int16_t* s_pred = reinterpret_cast<int16_t*>(take(N * 2));
+  int16_t* s_succ = reinterpret_cast<int16_t*>(take(N * 2));
+  int16_t* s_endf = reinterpret_cast<int16_t*>(take(N * 2));
+  int16_t* s_endr = reinterpret_cast<int16_t*>(take(N * 2));
+  uint8_t* s_vis = take(N);
+  int* s_cnt = reinterpret_cast<int*>(take(16));
+  int16_t* s_plan = reinterpret_cast<int16_t*>(take((size_t)K * L * 2));
+  float* s_mean = reinterpret_cast<float*>(take((size_t)K * 128 * 4));
+  float* s_te = reinterpret_cast<float*>(take((size_t)K * 256 * 4));
+  float* s_q = reinterpret_cast<float*>(take(512 * 4));
+  float* s_ctxt = reinterpret_cast<float*>(take(256 * 4));
+  float* s_qp = reinterpret_cast<float*>(take(4 * QP_STRIDE * 4));
+  float* s_gbar = reinterpret_cast<float*>(take(4 * QP_STRIDE * 4));
+  float* s_g = reinterpret_cast<float*>(take(256 * 4));
+  float* s_lp = reinterpret_cast<float*>(take(256 * 4));
+  float* s_sn = reinterpret_cast<float*>(take(4 * 128 * 4));
+  float* s_ln = reinterpret_cast<float*>(take(128 * 4));
+  float* s_pn = reinterpret_cast<float*>(take(4 * 128 * 4));
+  float* s_qt = reinterpret_cast<float*>(take(4 * JAMPR_MAX_SLOTS * 4));
+  float* s_lt = reinterpret_cast<float*>(take(JAMPR_MAX_SLOTS * 4));
+  float* s_P = reinterpret_cast<float*>(take(4 * JAMPR_MAX_SLOTS * 4));
+  float* s_sc = reinterpret_cast<float*>(take((size_t)4 * A * 4));
+  float* s_logit = reinterpret_cast<float*>(take((size_t)A * 4));
+  float* s_feat = reinterpret_cast<float*>(take((size_t)K * 8 * 4));
+  int* s_nbh = reinterpret_cast<int*>(take((size_t)A * 4));
+  uint8_t* s_mask = take(A);
+  int* s_idx = reinterpret_cast<int*>(take(JAMPR_MAX_SLOTS * 4));
+  uint64_t* full = bars;
+  uint64_t* bar_root = bars + 4;
+  uint64_t* bar_acc = bars + 5;
+
+  // ---------------------------------------------------------------- prologue
+  if (fresh) {
+    if (tid == 0) {
+      for (int i = 0; i < 4; ++i) mbar_init(&full[i], 1);
+      mbar_init(bar_root, 1);
+      mbar_init(bar_acc, 1);
+      mbar_fence_init();
+      for (int s = 0; s < 4; ++s) load_w_stage<T>(sW, s, a.w16, 0, full);
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    // zero the operand tiles: rows >= N stay zero for the whole kernel
+    for (int e = tid; e < 65536 / 16; e += PT_THREADS) reinterpret_cast<uint4*>(sA)[e] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (tid < 4) s_cnt[tid] = 0;
+  // tour features (env.py:1061-1068), tour buffer rows of the active vehicles and their lengths
+  if (tid < K) {
+    const size_t bk = (size_t)b * K + tid;
+    const int row = st.row[bk];
+    s_feat[tid * 8 + 0] = (float)st.cur[bk];
+    s_feat[tid * 8 + 1] = st.cap[bk];
+    s_feat[tid * 8 + 2] = st.time[bk];
+    s_feat[tid * 8 + 3] = st.cttd[bk];
+    s_feat[tid * 8 + 4] = (float)(d.k_max - row) / (float)d.k_max;
+  }
+  for (int e = tid; e < K * L; e += PT_THREADS) {
+    const int t = e / L, q = e - t * L;
+    s_plan[e] = st.plan[((size_t)b * d.k_max + st.row[(size_t)b * K + t]) * L + q];
+  }
+  for (int e = tid; e < A; e += PT_THREADS) {
+    s_nbh[e] = st.nbh[(size_t)b * A + e];
+    s_mask[e] = st.mask[(size_t)b * A + e];
+  }
+  __syncthreads();
+  if (fresh) {
+    const int16_t* gk = p.knn + (size_t)ins * N * k;
+    const float* gw = p.knn_w + (size_t)ins * N * k;
+    for (int e = tid; e < N * k; e += PT_THREADS)
+      s_tab[e] = (uint32_t)(uint16_t)gk[e] | ((uint32_t)bits_T<T>(gw[e]) << 16);
+    const float* dist = p.dist + (size_t)ins * N * N;
+    for (int u = tid; u < N; u += PT_THREADS) {
+      const int pr = st.pred[(size_t)b * N + u], su = st.succ[(size_t)b * N + u];
+      const int vs = st.visited[(size_t)b * N + u];
+      s_pred[u] = (int16_t)pr;
+      s_succ[u] = (int16_t)su;
+      s_vis[u] = (uint8_t)vs;
+      s_wpred[u] = to_T<T>(dist[(size_t)u * N + pr]);
+      s_wsucc[u] = to_T<T>(dist[(size_t)u * N + su]);
+      s_ttd[u] = to_T<T>(p.ttd[(size_t)ins * N + u]);
+      if (u > 0 && vs) {
+        if (su == 0) s_endf[atomicAdd(&s_cnt[0], 1)] = (int16_t)u;
+        if (pr == 0) s_endr[atomicAdd(&s_cnt[1], 1)] = (int16_t)u;
+      }
+    }
+  }
+  if (tid < K) {
+    int idx = 0;
+    while (idx < L && s_plan[tid * L + idx] != 0) ++idx;
+    s_idx[tid] = (idx >= L) ? 0 : idx;        // argmin over an all-nonzero row is position 0 (tour_encoder.py:236)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const int q4 = warp & 3, cg = warp >> 2, r = q4 * 32 + lane;      // epilogue role: row r, columns 32cg..32cg+31
+
+  if (fresh) {
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t idesc = umma_idesc(128, 128, Elem<T>::fmt);
+    const uint32_t a_addr = smem_u32(sA), w_addr = smem_u32(sW);
+    // ---- h_0 = node_emb_input_proj(static_emb) (hoisted, per instance): fp32 -> TMEM skip columns, 16-bit -> h tiles
+    {
+      uint32_t hv[32];
+      if (r < N) {
+        const float4* src = reinterpret_cast<const float4*>(p.h0 + ((size_t)ins * N + r) * 128 + cg * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = __ldg(src + i);
+          hv[4 * i] = __float_as_uint(v.x); hv[4 * i + 1] = __float_as_uint(v.y);
+          hv[4 * i + 2] = __float_as_uint(v.z); hv[4 * i + 3] = __float_as_uint(v.w);
+        }
+        uint8_t* tile = sA + (2 + (cg >> 1)) * 16384;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            pk[e] = as_u32(Elem<T>::from2(__uint_as_float(hv[i * 8 + 2 * e]), __uint_as_float(hv[i * 8 + 2 * e + 1])));
+          *reinterpret_cast<uint4*>(tile + sw128_off(r, (cg & 1) * 4 + i)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) hv[i] = 0u;
+      }
+      tmem_st32(ta + 128 + cg * 32, hv);
+      tmem_wait_st();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const int n_endf = s_cnt[0], n_endr = s_cnt[1];
+    for (int l = 0; l < 6; ++l) {
+      const uint32_t ph = (uint32_t)(l & 1);
+      if (tid == 0) {
+        // lin_root(h): K-blocks 2,3 — overlaps the aggregation below
+        mbar_wait(&full[2], ph);
+        mbar_wait(&full[3], ph);
+        tc_fence_after();
+        mma_kblock(tmem, a_addr + 2 * 16384, w_addr + 2 * 16384, idesc, true);
+        mma_kblock(tmem, a_addr + 3 * 16384, w_addr + 3 * 16384, idesc, false);
+        umma_commit(bar_root);
+      }
+      if (l == 2 || l == 5) agg_nbh_tc<T>(sA, s_tab, s_ttd, N, k);
+      else if (l < 2) agg_tour_tc<T>(sA, s_vis, s_pred, s_wpred, s_endf, n_endf, s_ttd, N);
+      else agg_tour_tc<T>(sA, s_vis, s_succ, s_wsucc, s_endr, n_endr, s_ttd, N);
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(bar_root, ph);                       // stages 2,3 are free: stream the next layer into them
+        load_w_stage<T>(sW, 2, a.w16, l + 1, full);
+        load_w_stage<T>(sW, 3, a.w16, l + 1, full);
+        mbar_wait(&full[0], ph);
+        mbar_wait(&full[1], ph);
+        tc_fence_after();
+        mma_kblock(tmem, a_addr, w_addr, idesc, false);
+        mma_kblock(tmem, a_addr + 16384, w_addr + 16384, idesc, false);
+        umma_commit(bar_acc);
+      }
+      mbar_wait(bar_acc, ph);
+      tc_fence_after();
+      if (tid == 0) {
+        load_w_stage<T>(sW, 0, a.w16, l + 1, full);
+        load_w_stage<T>(sW, 1, a.w16, l + 1, full);
+      }
+      layer_epilogue<T>(tmem, sA, s_red, w + OFF_TE_BLK + (size_t)l * BLK_FLOATS, N,
+                        (l == 5 && a.store_cache) ? st.h_fin + (size_t)b * N * 128 : nullptr);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+    // ---- node_emb_output_proj: D[:, 0:128] = h W_o[0:128]^T (stages 0,1), D[:, 128:256] = h W_o[128:256]^T (stages 2,3)
+    if (tid == 0) {
+      for (int s = 0; s < 4; ++s) mbar_wait(&full[s], 0u);
+      tc_fence_after();
+      mma_kblock(tmem, a_addr + 2 * 16384, w_addr, idesc, true);
+      mma_kblock(tmem, a_addr + 3 * 16384, w_addr + 16384, idesc, false);
+      mma_kblock(tmem + 128, a_addr + 2 * 16384, w_addr + 2 * 16384, idesc, true);
+      mma_kblock(tmem + 128, a_addr + 3 * 16384, w_addr + 3 * 16384, idesc, false);
+      umma_commit(bar_acc);
+    }
+  } else {
+    // cached tour-graph embedding (tour_encoder.py:163-166): h_fin -> h tiles (for the per-tour means below)
+    for (int e = tid; e < N * 16; e += PT_THREADS) {
+      const int u = e >> 4, cc = e & 15;
+      const float4* src = reinterpret_cast<const float4*>(st.h_fin + ((size_t)b * N + u) * 128 + cc * 8);
+      const float4 v0 = src[0], v1 = src[1];
+      *reinterpret_cast<uint4*>(sA + (2 + (cc >> 3)) * 16384 + sw128_off(u, cc & 7)) =
+          make_uint4(as_u32(Elem<T>::from2(v0.x, v0.y)), as_u32(Elem<T>::from2(v0.z, v0.w)),
+                     as_u32(Elem<T>::from2(v1.x, v1.y)), as_u32(Elem<T>::from2(v1.z, v1.w)));
+    }
+    __syncthreads();
+  }
+
+  // ---------------------------------------------------------------- per-tour mean of h over the buffer positions
+  // 0..idx (includes one depot entry, tour_encoder.py:236-243); overlaps the projection MMAs
+  for (int e = tid; e < K * 64; e += PT_THREADS) {
+    const int t = e >> 6, c2 = e & 63;              // feature pair 2*c2, 2*c2+1
+    const uint32_t off = (uint32_t)(2 + (c2 >> 5)) * 16384u;
+    const uint32_t ch = (uint32_t)(c2 & 31) >> 2, within = (uint32_t)(c2 & 3) * 4u;
+    const int idx = s_idx[t];
+    float sx = 0.0f, sy = 0.0f;
+    for (int q = 0; q <= idx; ++q) {
+      const uint32_t u = (uint32_t)s_plan[t * L + q];
+      const float2 v = Elem<T>::to2(*reinterpret_cast<const T2*>(sA + off + sw128_off(u, ch) + within));
+      sx += v.x;
+      sy += v.y;
+    }
+    const float inv = 1.0f / (float)(idx + 1);
+    s_mean[t * 128 + 2 * c2] = sx * inv;
+    s_mean[t * 128 + 2 * c2 + 1] = sy * inv;
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- node embedding rows -> shared memory (fp32)
+  if (fresh) {
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16);
+    mbar_wait(bar_acc, 0u);
+    tc_fence_after();
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t acc[32];
+      tmem_ld32_nowait(ta + hf * 128 + cg * 32, acc);
+      tmem_wait_ld();
+      if (r < N) {
+        const int c0 = hf * 128 + cg * 32;
+        const float4* se = reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + r) * 256 + c0);
+        const float4* bo = reinterpret_cast<const float4*>(w + OFF_TE_OUT_B + c0);
+        float4* dst = reinterpret_cast<float4*>(s_ne + (size_t)r * NE_STRIDE + c0);
+        float4* gdst = a.store_cache ? reinterpret_cast<float4*>(st.ne + ((size_t)b * N + r) * 256 + c0) : nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 s4 = __ldg(se + i), b4 = __ldg(bo + i);
+          const float4 v = make_float4(__uint_as_float(acc[4 * i]) + b4.x + s4.x, __uint_as_float(acc[4 * i + 1]) + b4.y + s4.y,
+                                       __uint_as_float(acc[4 * i + 2]) + b4.z + s4.z, __uint_as_float(acc[4 * i + 3]) + b4.w + s4.w);
+          dst[i] = v;
+          if (gdst) gdst[i] = v;
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    for (int e = tid; e < N * 64; e += PT_THREADS) {
+      const int u = e >> 6, c4 = (e & 63) * 4;
+      *reinterpret_cast<float4*>(s_ne + (size_t)u * NE_STRIDE + c4) =
+          *reinterpret_cast<const float4*>(st.ne + ((size_t)b * N + u) * 256 + c4);
+    }
+  }
+  __syncthreads();
+  if (fresh && warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(*tmem_slot, 256);
+  }
+
+  // ---------------------------------------------------------------- decoder
+  // (b) tour_emb[t] = folded tour-feature branch + W_to2 mean_h[t]          (tour_encoder.py:202-213)
+  matvec_partial<T, 2, 4>(w16 + W16_TO2, 128, s_mean, 128, s_part);   // NV = 4 >= K slots (K <= 4 on this path)
+  // (a) column mean / max of node_emb over the nodes (policy.py:179-181) — independent of (b)
+  float nmean = 0.0f, nmax = -INFINITY;
+  if (tid < 256) {
+    for (int u = 0; u < N; ++u) {
+      const float v = s_ne[(size_t)u * NE_STRIDE + tid];
+      nmean += v;
+      nmax = fmaxf(nmax, v);
+    }
+    nmean /= (float)N;
+    if (a.store_cache && fresh) {
+      st.ne_stats[(size_t)b * 512 + tid] = nmean;
+      st.ne_stats[(size_t)b * 512 + 256 + tid] = nmax;
+    }
+  }
+  __syncthreads();
+  if (tid < 256) {
+    float sm = 0.0f, mx = -INFINITY;
+    for (int t = 0; t < K; ++t) {
+      float v = __ldg(w + OFF_TOF_B + tid);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) v = fmaf(s_feat[t * 8 + i], __ldg(w + OFF_TOF_WT + i * 256 + tid), v);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) v += s_part[(ks * 4 + t) * 256 + tid];
+      s_te[t * 256 + tid] = v;
+      sm += v;
+      mx = fmaxf(mx, v);
+    }
+    s_q[tid] = nmean + sm / (float)K;
+    s_q[256 + tid] = nmax + mx;
+  }
+  __syncthreads();
+  // (c) ctxt = ctxt_proj(query)
+  matvec_partial<T, 8, 1>(w16 + W16_CTXT, 512, s_q, 0, s_part);
+  __syncthreads();
+  if (tid < 256) {
+    float v = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) v += s_part[ks * 256 + tid];
+    s_ctxt[tid] = v;
+  }
+  __syncthreads();
+  // (d) qp[h] = W_gk,h^T ctxt_h : K-slice ks (16 rows of set_proj) belongs to head ks / 4
+  matvec_partial<T, 8, 1>(w16 + W16_GK, 256, s_ctxt, 0, s_part);
+  __syncthreads();
+  for (int e = tid; e < 1024; e += PT_THREADS) {
+    const int h = e >> 8, c = e & 255;
+    s_qp[h * QP_STRIDE + c] = s_part[(4 * h) * 256 + c] + s_part[(4 * h + 1) * 256 + c] + s_part[(4 * h + 2) * 256 + c] +
+                              s_part[(4 * h + 3) * 256 + c];
+  }
+  __syncthreads();
+  // (e) per-node and per-tour glimpse scores qp_h . node_emb[n], qp_h . tour_emb[t]
+  for (int n = warp; n < N + K; n += PT_THREADS / 32) {
+    const float* row = (n < N) ? (s_ne + (size_t)n * NE_STRIDE) : (s_te + (n - N) * 256);
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      const float v = row[c];
+      d0 = fmaf(v, s_qp[c], d0);
+      d1 = fmaf(v, s_qp[QP_STRIDE + c], d1);
+      d2 = fmaf(v, s_qp[2 * QP_STRIDE + c], d2);
+      d3 = fmaf(v, s_qp[3 * QP_STRIDE + c], d3);
+    }
+    d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
+    if (lane == 0) {
+      if (n < N) { s_sn[n] = d0; s_sn[128 + n] = d1; s_sn[256 + n] = d2; s_sn[384 + n] = d3; }
+      else { const int t = n - N; s_qt[t] = d0; s_qt[8 + t] = d1; s_qt[16 + t] = d2; s_qt[24 + t] = d3; }
+    }
+  }
+  __syncthreads();
+  // (f) glimpse scores per action, softmax per head
+  for (int e = tid; e < 4 * A; e += PT_THREADS) {
+    const int h = e / A, aa = e - h * A;
+    const float sc = (s_sn[h * 128 + s_nbh[aa]] + s_qt[h * 8 + aa / k]) * 0.125f;
+    s_sc[e] = s_mask[aa] ? -INFINITY : sc;
+  }
+  __syncthreads();
+  if (warp < JAMPR_HEADS) {
+    float* sc = s_sc + warp * A;
+    float mx = -INFINITY;
+    for (int e = lane; e < A; e += 32) mx = fmaxf(mx, sc[e]);
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int e = lane; e < A; e += 32) {
+      const float ex = expf(sc[e] - mx);
+      sc[e] = ex;
+      sum += ex;
+    }
+    sum = warp_sum(sum);
+    for (int e = lane; e < A; e += 32) sc[e] = sc[e] / sum;
+  }
+  __syncthreads();
+  // glimpse weights folded onto nodes and tours (fixed summation order: deterministic)
+  for (int e = tid; e < 4 * N; e += PT_THREADS) {
+    const int h = e / N, n = e - h * N;
+    float acc = 0.0f;
+    for (int aa = 0; aa < A; ++aa)
+      if (s_nbh[aa] == n) acc += s_sc[h * A + aa];
+    s_pn[h * 128 + n] = acc;
+  }
+  if (tid < 4 * K) {
+    const int h = tid / K, t = tid - h * K;
+    float acc = 0.0f;
+    for (int j = 0; j < k; ++j) acc += s_sc[h * A + t * k + j];
+    s_P[h * 8 + t] = acc;
+  }
+  __syncthreads();
+  // (g) gbar[h] = sum_a p[h][a] act[a] = sum_t P[h][t] tour_emb[t] + sum_n pn[h][n] node_emb[n]
+  {
+    const int c = tid & 255, half = tid >> 8;
+    float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+    for (int n = half; n < N; n += 2) {
+      const float v = s_ne[(size_t)n * NE_STRIDE + c];
+      g0 = fmaf(s_pn[n], v, g0);
+      g1 = fmaf(s_pn[128 + n], v, g1);
+      g2 = fmaf(s_pn[256 + n], v, g2);
+      g3 = fmaf(s_pn[384 + n], v, g3);
+    }
+    if (half == 0) {
+      for (int t = 0; t < K; ++t) {
+        const float v = s_te[t * 256 + c];
+        g0 = fmaf(s_P[t], v, g0);
+        g1 = fmaf(s_P[8 + t], v, g1);
+        g2 = fmaf(s_P[16 + t], v, g2);
+        g3 = fmaf(s_P[24 + t], v, g3);
+      }
+    }
+    s_part[(half * 4 + 0) * 256 + c] = g0;
+    s_part[(half * 4 + 1) * 256 + c] = g1;
+    s_part[(half * 4 + 2) * 256 + c] = g2;
+    s_part[(half * 4 + 3) * 256 + c] = g3;
+  }
+  __syncthreads();
+  for (int e = tid; e < 1024; e += PT_THREADS) {
+    const int h = e >> 8, c = e & 255;
+    s_gbar[h * QP_STRIDE + c] = s_part[h * 256 + c] + s_part[(4 + h) * 256 + c];
+  }
+  __syncthreads();
+  // (h) glimpse g[o] = W_gv[o] . gbar[head(o)]
+  matvec_partial<T, 8, 1>(w16 + W16_GV, 256, s_gbar + ((tid & 31) >> 3) * QP_STRIDE, 0, s_part);
+  __syncthreads();
+  if (tid < 256) {
+    float v = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) v += s_part[ks * 256 + tid];
+    s_g[tid] = v;
+  }
+  __syncthreads();
+  // (i) lp = W_lk^T out_proj(g) = M1 g
+  matvec_partial<T, 8, 1>(w16 + W16_M1, 256, s_g, 0, s_part);
+  __syncthreads();
+  if (tid < 256) {
+    float v = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) v += s_part[ks * 256 + tid];
+    s_lp[tid] = v;
+  }
+  __syncthreads();
+  // (j) pointer logits: 10 tanh((lp . node_emb[n] + lp . tour_emb[t]) / 16)
+  for (int n = warp; n < N + K; n += PT_THREADS / 32) {
+    const float* row = (n < N) ? (s_ne + (size_t)n * NE_STRIDE) : (s_te + (n - N) * 256);
+    float dd = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      dd = fmaf(row[c], s_lp[c], dd);
+    }
+    dd = warp_sum(dd);
+    if (lane == 0) {
+      if (n < N) s_ln[n] = dd;
+      else s_lt[n - N] = dd;
+    }
+  }
+  __syncthreads();
+  for (int aa = tid; aa < A; aa += PT_THREADS)
+    s_logit[aa] = s_mask[aa] ? -INFINITY : 10.0f * tanhf((s_ln[s_nbh[aa]] + s_lt[aa / k]) * 0.0625f);
+  __syncthreads();
+  // ---- log-softmax + selection (warp 0), same rules as decoder.cu
+  if (warp == 0) {
+    float mx = -INFINITY;
+    bool nan = false;
+    for (int e = lane; e < A; e += 32) {
+      const float v = s_logit[e];
+      nan |= (v != v);
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int e = lane; e < A; e += 32) sum += expf(s_logit[e] - mx);
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    float ent = 0.0f, best = -INFINITY;
+    int besti = 0x7fffffff;
+    for (int e = lane; e < A; e += 32) {
+      const float lpv = s_logit[e] - lse;
+      nan |= (lpv != lpv);
+      s_logit[e] = lpv;
+      if (st.logp) st.logp[(size_t)b * A + e] = lpv;
+      if (lpv >= -10000.0f) ent -= lpv * expf(lpv);
+      if (lpv > best) { best = lpv; besti = e; }
+    }
+    nan = __any_sync(0xffffffffu, nan);
+    ent = warp_sum(ent);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    int choice = besti;
+    if (a.decode_type == JAMPR_DECODE_SAMPLING) {
+      const float u = a.uniforms ? a.uniforms[b] : jampr_uniform(a.seed, (uint32_t)b, (uint32_t)a.step_no);
+      float run = 0.0f;
+      int hit = -1, lastf = -1;
+      for (int bs0 = 0; bs0 < A; bs0 += 32) {
+        const int e = bs0 + lane;
+        const float pe = (e < A) ? expf(s_logit[e]) : 0.0f;
+        float inc = pe;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const float cum = run + inc;
+        const unsigned hm = __ballot_sync(0xffffffffu, e < A && pe > 0.0f && cum > u);
+        const unsigned fm = __ballot_sync(0xffffffffu, e < A && pe > 0.0f);
+        if (hit < 0 && hm) hit = bs0 + __ffs(hm) - 1;
+        if (fm) lastf = bs0 + 31 - __clz(fm);
+        run = __shfl_sync(0xffffffffu, cum, 31);
+      }
+      choice = (hit >= 0) ? hit : lastf;
+      if (choice < 0) choice = 0;
+    }
+    if (lane == 0) {
+      if (choice >= A) choice = 0;
+      st.action[2 * (size_t)b] = choice / k;
+      st.action[2 * (size_t)b + 1] = s_nbh[choice];
+      st.ll[b] = s_logit[choice];
+      st.entropy[b] = ent;
+      if (nan) atomicOr(st.status + b, JAMPR_ST_NAN_LOGITS);
+    }
+  }
+}
+
+static size_t pt_smem_bytes(const jampr_dims_t* d) {
+  const size_t N = d->n_nodes, k = d->k_nbh, K = d->n_slots, A = K * k, L = d->plan_len;
+  auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
+  size_t s = 1024 + OVERLAY_BYTES;
+  s += al(64) + al(16) + al(4 * 128 * 8) + al(16 * 256 * 4) + al(N * k * 4);
+  s += 7 * al(N * 2) + al(N) + al(16) + al(K * L * 2) + al(K * 128 * 4) + al(K * 256 * 4) + al(512 * 4) + al(256 * 4);
+  s += 2 * al(4 * QP_STRIDE * 4) + 2 * al(256 * 4) + al(4 * 128 * 4) + al(128 * 4) + al(4 * 128 * 4);
+  s += al(4 * JAMPR_MAX_SLOTS * 4) + al(JAMPR_MAX_SLOTS * 4) + al(4 * JAMPR_MAX_SLOTS * 4) + al(4 * A * 4) + al(A * 4);
+  s += al(K * 8 * 4) + al(A * 4) + al(A) + al(JAMPR_MAX_SLOTS * 4);
+  return s;
+}
+
+int64_t jampr_w16_elems(void) { return (int64_t)W16_END; }
+
+template <typename T>
+static int launch_pt(const PtArgs& a, size_t smem, cudaStream_t s) {
+  CUDA_RET(cudaFuncSetAttribute(policy_step_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  policy_step_tc_kernel<T><<<a.d.n_inst * a.d.n_samples, PT_THREADS, smem, s>>>(a);
+  return launch_status();
+}
+
+// One fused policy step on the tensor-core path.  store_cache: also write h_fin / ne / ne_stats (fp32) to HBM.
+int jampr_policy_step_tc(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                         const jampr_state_t* st, int graph_fresh, int step_no, int decode_type, uint64_t seed,
+                         const float* uniforms, int store_cache, cudaStream_t s) {
+  if (d->n_nodes > 128 || d->n_slots > 4 || d->k_nbh > 255) return JAMPR_E_TOOLARGE;
+  if (!w->blob_bf16 || w->n_bf16 < (int64_t)W16_END) return JAMPR_E_BADARG;
+  const size_t smem = pt_smem_bytes(d);
+  if (smem > 227 * 1024) return JAMPR_E_TOOLARGE;
+  PtArgs a;
+  a.d = *d;
+  a.p = *inst;
+  a.st = *st;
+  a.w = w->blob;
+  a.w16 = w->blob_bf16;
+  a.uniforms = uniforms;
+  a.seed = seed;
+  a.step_no = step_no;
+  a.decode_type = decode_type;
+  a.graph_fresh = graph_fresh;
+  a.store_cache = store_cache;
+  if (w->precision == JAMPR_PREC_F16) return launch_pt<__half>(a, smem, s);
+  return launch_pt<__nv_bfloat16>(a, smem, s);
+}

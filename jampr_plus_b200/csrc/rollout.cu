@@ -9,27 +9,29 @@ int jampr_tour_encoder_f32(const jampr_dims_t*, const jampr_instances_t*, const 
                            cudaStream_t);
 int jampr_decoder_launch(const jampr_dims_t*, const jampr_instances_t*, const jampr_state_t*, const float*, int, int,
                          uint64_t, const float*, cudaStream_t);
-int jampr_node_encoder_tc(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, cudaStream_t);
-int jampr_tour_encoder_tc(const jampr_dims_t*, const jampr_instances_t*, const jampr_state_t*,
-                          const jampr_weights_t*, int, cudaStream_t);
+int jampr_policy_step_tc(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, const jampr_state_t*,
+                         int, int, int, uint64_t, const float*, int, cudaStream_t);
+int64_t jampr_w16_elems(void);
 
 static int check_policy_args(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w) {
   if (!d || !inst || !w || !w->blob || w->n_floats < (int64_t)OFF_END) return JAMPR_E_BADARG;
   if (d->n_inst <= 0 || d->n_samples <= 0 || d->n_nodes < 2 || d->n_slots <= 0 || d->n_slots > JAMPR_MAX_SLOTS ||
       d->k_nbh < 2 || d->k_nbh > d->n_nodes)
     return JAMPR_E_BADARG;
-  if (w->precision != JAMPR_PREC_F32 && w->precision != JAMPR_PREC_BF16) return JAMPR_E_BADARG;
-  if (w->precision == JAMPR_PREC_BF16 && !w->blob_bf16) return JAMPR_E_BADARG;
+  if (w->precision != JAMPR_PREC_F32 && w->precision != JAMPR_PREC_BF16 && w->precision != JAMPR_PREC_F16)
+    return JAMPR_E_BADARG;
+  if (w->precision != JAMPR_PREC_F32 && (!w->blob_bf16 || w->n_bf16 < jampr_w16_elems())) return JAMPR_E_BADARG;
   return 0;
 }
 
 extern "C" int64_t jampr_weight_blob_floats(void) { return (int64_t)OFF_END; }
+extern "C" int64_t jampr_weight_blob16_elems(void) { return jampr_w16_elems(); }
 
 extern "C" int jampr_weight_offsets(int64_t* out, int32_t max_entries) {
   static const int64_t offs[] = {OFF_NE_IN_WT, OFF_NE_IN_B, OFF_NE_BLK, OFF_NE_OUT_WT, OFF_NE_OUT_B, OFF_TE_IN_WT,
                                  OFF_TE_IN_B, OFF_TE_BLK, OFF_TE_OUT_WT, OFF_TE_OUT_B, OFF_TF_WT, OFF_TF_B,
                                  OFF_TO_WT, OFF_TO_B, OFF_CTXT_WT, OFF_GK_W, OFF_GV_WT, OFF_LK_W, OFF_OUT_WT,
-                                 OFF_END, BLK_FLOATS};
+                                 OFF_TOF_WT, OFF_TOF_B, OFF_END, BLK_FLOATS};
   const int n = (int)(sizeof(offs) / sizeof(offs[0]));
   if (!out || max_entries < n) return JAMPR_E_BADARG;
   for (int i = 0; i < n; ++i) out[i] = offs[i];
@@ -40,7 +42,8 @@ extern "C" int jampr_node_encoder(const jampr_dims_t* d, const jampr_instances_t
                                   void* stream) {
   const int rc = check_policy_args(d, inst, w);
   if (rc) return rc;
-  if (w->precision == JAMPR_PREC_BF16) return jampr_node_encoder_tc(d, inst, w, (cudaStream_t)stream);
+  // once per episode and < 1 % of it: every precision runs the fp32 kernel, the tensor-core step kernel
+  // converts h0 / static_emb on the fly
   return jampr_node_encoder_f32(d, inst, w->blob, (cudaStream_t)stream);
 }
 
@@ -50,8 +53,11 @@ extern "C" int jampr_tour_encoder(const jampr_dims_t* d, const jampr_instances_t
   if (rc) return rc;
   if (!st || !st->h_fin || !st->ne || !st->ne_stats) return JAMPR_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
-  return (w->precision == JAMPR_PREC_BF16) ? jampr_tour_encoder_tc(d, inst, st, w, step_no, s)
-                                           : jampr_tour_encoder_f32(d, inst, st, w->blob, step_no, s);
+  // on the tensor-core path the encoder is fused with the decoder: the call runs the whole policy step (greedy)
+  // and additionally stores h_fin / ne / ne_stats
+  if (w->precision != JAMPR_PREC_F32)
+    return jampr_policy_step_tc(d, inst, w, st, 1, step_no, JAMPR_DECODE_GREEDY, 0, nullptr, 1, s);
+  return jampr_tour_encoder_f32(d, inst, st, w->blob, step_no, s);
 }
 
 extern "C" int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
@@ -62,9 +68,11 @@ extern "C" int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t*
   if (!st || (decode_type != JAMPR_DECODE_GREEDY && decode_type != JAMPR_DECODE_SAMPLING)) return JAMPR_E_BADARG;
   if (!st->h_fin || !st->ne || !st->ne_stats) return JAMPR_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (w->precision != JAMPR_PREC_F32)
+    return jampr_policy_step_tc(d, inst, w, st, graph_fresh, step_no, decode_type, seed, uniforms,
+                                (d->upd_step != 1) || st->logp != nullptr, s);
   if (graph_fresh) {
-    rc = (w->precision == JAMPR_PREC_BF16) ? jampr_tour_encoder_tc(d, inst, st, w, step_no, s)
-                                           : jampr_tour_encoder_f32(d, inst, st, w->blob, step_no, s);
+    rc = jampr_tour_encoder_f32(d, inst, st, w->blob, step_no, s);
     if (rc) return rc;
   }
   return jampr_decoder_launch(d, inst, st, w->blob, step_no, decode_type, seed, uniforms, s);

@@ -14,7 +14,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from .. import _cabi
-from ..packing import pack_bf16, pack_f32
+from ..packing import pack_f32, pack_tc
 from ..routing.formats import RPObs
 
 __all__ = ["Policy", "GNN_ATTN_POLICY_CFG"]
@@ -90,8 +90,9 @@ class _Decoder(nn.Module):       # attn_decoder.py:49-54
 class Policy(nn.Module):
     """Drop-in for reference ``lib.model.Policy`` (policy.py:19-240) for the gnn_attn architecture.
 
-    Extra keyword (not in the reference): ``precision`` = ``"fp32"`` (CUDA-core path, the 1e-5 parity anchor)
-    or ``"bf16"`` (tcgen05 tensor-core GEMMs with fp32 accumulation and epilogues)."""
+    Extra keyword (not in the reference): ``precision`` = ``"fp32"`` (CUDA-core path, the 1e-5 parity anchor),
+    ``"bf16"`` or ``"fp16"`` (tcgen05 tensor-core GEMMs on 16-bit operands with fp32 accumulation, epilogues and
+    skip connections; fp16 keeps 3 more significand bits at the same speed)."""
 
     def __init__(self,
                  observation_space: Dict,
@@ -113,8 +114,8 @@ class Policy(nn.Module):
         _check_cfg("node_encoder_args", node_encoder_args, GNN_ATTN_POLICY_CFG["node_encoder_args"])
         _check_cfg("tour_encoder_args", tour_encoder_args, GNN_ATTN_POLICY_CFG["tour_encoder_args"])
         _check_cfg("decoder_args", decoder_args, GNN_ATTN_POLICY_CFG["decoder_args"])
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "bf16", "fp16"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
         self.observation_space = observation_space
         self.embedding_dim = embedding_dim
         self.precision = precision
@@ -161,7 +162,10 @@ class Policy(nn.Module):
         if self._blob is None or key != self._blob_key:
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             self._blob = pack_f32(sd).to(self._device)
-            self._blob_bf16 = pack_bf16(sd).to(self._device) if self.precision == "bf16" else None
+            self._blob_bf16 = None
+            if self.precision != "fp32":
+                self._blob_bf16 = pack_tc(sd, torch.bfloat16 if self.precision == "bf16" else torch.float16) \
+                    .to(self._device)
             self._blob_key = key
             self._static_key = None
         w = _cabi.Weights()
@@ -169,7 +173,7 @@ class Policy(nn.Module):
         w.n_floats = self._blob.numel()
         w.blob_bf16 = _cabi.ptr(self._blob_bf16)
         w.n_bf16 = 0 if self._blob_bf16 is None else self._blob_bf16.numel()
-        w.precision = _cabi.PREC_BF16 if self.precision == "bf16" else _cabi.PREC_F32
+        w.precision = {"fp32": _cabi.PREC_F32, "bf16": _cabi.PREC_BF16, "fp16": _cabi.PREC_F16}[self.precision]
         return w
 
     def _decode_code(self) -> int:

@@ -69,6 +69,13 @@ def pack_f32(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     put("GV_WT", sp[256:512].t())
     put("LK_W", sp[512:768])
     put("OUT_WT", sd["decoder.out_proj.weight"].t())
+    # tensor-core path: the tour-feature branch of tour_encoder.output_proj folded into a 5 x 256 matrix
+    wto = sd["tour_encoder.output_proj.weight"].double()
+    tof = torch.zeros(8, 256)
+    tof[:5] = (wto[:, :128] @ sd["tour_encoder.input_proj.weight"].double()).t().float()
+    put("TOF_WT", tof)
+    put("TOF_B", (wto[:, :128] @ sd["tour_encoder.input_proj.bias"].double()
+                  + sd["tour_encoder.output_proj.bias"].double()).float())
     return blob
 
 
@@ -89,6 +96,31 @@ def sw128_image(w: torch.Tensor) -> torch.Tensor:
     return img.permute(1, 0, 2, 3).contiguous().view(-1).view(w.dtype)
 
 
-def pack_bf16(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
-    """bf16 GEMM operands for the tensor-core path (layout owned by csrc/encoder_tc.cu)."""
-    raise NotImplementedError("bf16 tensor-core path not built yet")
+def pack_tc(sd: Dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """16-bit operands of the tensor-core policy step (layout owned by csrc/policy_tc.cu, W16_*):
+
+    * 7 x 4 weight stages of 16 KB, each the swizzled shared-memory image of a [128 rows][64 K] tile: for the six
+      GraphConv blocks (tour_layers 0..2, rev_tour_layers 0..2) the B operand is cat([lin_rel.weight,
+      lin_root.weight], dim=1) (128 x 256; K-blocks 0,1 multiply the aggregated messages, 2,3 the node itself);
+      then node_emb_output_proj.weight as two 128-row halves x two K-blocks;
+    * decoder mat-vec matrices stored [K][256] (input-major): per-tour-mean half of tour output_proj, ctxt_proj^T,
+      set_proj[0:256] as stored, set_proj[256:512]^T, and M1^T = out_proj^T @ set_proj[512:768] (computed in fp64)."""
+    assert dtype in (torch.bfloat16, torch.float16)
+    sd = {k: v.detach().to(torch.float32).cpu() for k, v in validate_state_dict(sd).items()}
+    parts = []
+    for prefix in [f"tour_encoder.tour_layers.{i}" for i in range(3)] + \
+                  [f"tour_encoder.rev_tour_layers.{i}" for i in range(3)]:
+        wcat = torch.cat((sd[f"{prefix}.conv.lin_rel.weight"], sd[f"{prefix}.conv.lin_root.weight"]), 1)   # (128, 256)
+        parts.append(sw128_image(wcat.to(dtype)))
+    wo = sd["tour_encoder.node_emb_output_proj.weight"]                                                  # (256, 128)
+    for half in range(2):
+        parts.append(sw128_image(wo[half * 128:(half + 1) * 128].contiguous().to(dtype)))
+    sp = sd["decoder.set_proj.weight"]
+    m1t = (sd["decoder.out_proj.weight"].double().t() @ sp[512:768].double()).float()
+    for m in (sd["tour_encoder.output_proj.weight"][:, 128:].t(), sd["decoder.ctxt_proj.weight"].t(), sp[0:256],
+              sp[256:512].t(), m1t):
+        parts.append(m.contiguous().to(dtype).reshape(-1))
+    blob = torch.cat(parts)
+    lib = _cabi.load_library()
+    assert blob.numel() == lib.jampr_weight_blob16_elems(), (blob.numel(), lib.jampr_weight_blob16_elems())
+    return blob

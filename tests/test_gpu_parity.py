@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 LOGP_RTOL = 1e-5     # north_star: log-probabilities within 1e-5 relative in fp32
 LOGP_ATOL = 3e-5     # absolute floor: fp32 op-order noise of a 6-layer GNN + attention on |logp| ~ 1..10
 DECISION_GAP = 2e-4  # decisions whose reference top-2 gap is below this may legitimately flip
+FINAL_COST_RTOL = 1e-6   # costs: north_star allows 1e-5 relative in fp32; only the terminal step is not bit-exact
 
 
 def _ieee_dist(g):
@@ -101,12 +102,24 @@ def test_teacher_forced_episode(name):
             err = np.abs(logp[fin] - ref[fin])
             assert (err <= LOGP_ATOL + LOGP_RTOL * np.abs(ref[fin])).all(), (t, float(err.max()))
             worst_rel = max(worst_rel, float((err / np.maximum(np.abs(ref[fin]), 1.0)).max()))
+            # the policy's own greedy pick must be the reference's wherever the reference's top-2 gap is decisive
+            if g["decode"] == "greedy":
+                srt = np.sort(ref, -1)
+                decisive = (srt[:, -1] - srt[:, -2]) > DECISION_GAP
+                mine = env.state["action"].cpu().numpy()
+                assert np.array_equal(mine[decisive], g["trace_action"][t][decisive]), f"greedy action step {t}"
             obs, cost, done, info = env.step(torch.from_numpy(g["trace_action"][t].astype(np.int64)))
-            assert np.array_equal(cost.cpu().numpy(), g["trace_cost"][t]), f"cost step {t}"
-            assert np.array_equal(env.total_cost.cpu().numpy(), g["trace_total"][t]), f"total step {t}"
+            if not done:
+                assert np.array_equal(cost.cpu().numpy(), g["trace_cost"][t]), f"cost step {t}"
+                assert np.array_equal(env.total_cost.cpu().numpy(), g["trace_total"][t]), f"total step {t}"
+            else:
+                # terminal step: return legs + the singleton penalties of all unvisited customers are SUMMED
+                # (env.py:287-295, torch.sum's own blocked order on the CPU) -> FINAL_COST_RTOL, not bit equality
+                np.testing.assert_allclose(cost.cpu().numpy(), g["trace_cost"][t], rtol=FINAL_COST_RTOL, atol=0)
+                np.testing.assert_allclose(env.total_cost.cpu().numpy(), g["trace_total"][t], rtol=FINAL_COST_RTOL, atol=0)
     assert done
     assert np.array_equal(env.tour_plan.cpu().numpy(), g["final_tour_plan"])
-    assert np.array_equal(env.total_cost.cpu().numpy(), g["final_total_cost"])
+    np.testing.assert_allclose(env.total_cost.cpu().numpy(), g["final_total_cost"], rtol=FINAL_COST_RTOL, atol=0)
     assert np.array_equal(env.k_used.cpu().numpy(), g["final_k_used"])
     assert np.array_equal(env._visited.cpu().numpy(), g["final_visited"])
     assert env._step == int(g["final_step"])
@@ -129,14 +142,17 @@ def test_fused_rollout_reproduces_reference_tours(name):
         total, info = rollout(pol, env)
     assert info["done_step"] == int(g["final_step"]) - 1
     plan = env.tour_plan.cpu().numpy()
-    assert decided.sum() >= 0.75 * decided.size, "fixture has too many near-ties to be a useful pin"
+    # every rollout without a near-tie anywhere along its ~N decisions must reproduce the reference tours exactly
+    # (rollouts with a near-tie are covered decision by decision in test_teacher_forced_episode)
+    assert decided.sum() >= 0.5 * decided.size, "fixture has too many near-ties to be a useful pin"
     assert np.array_equal(plan[decided], g["final_tour_plan"][decided])
-    if decided.all():
-        # identical batch -> identical reported totals (the batch-global finishing step matters)
-        assert np.array_equal(total.cpu().numpy(), g["final_total_cost"])
-    else:
-        tc = env.true_cost().cpu().numpy()
-        assert np.isfinite(tc).all()
+    # identical tours in an identical batch -> identical reported totals (the batch-global finishing step
+    # matters), up to the summation order of the terminal penalties
+    same = (plan == g["final_tour_plan"]).all(axis=(1, 2))
+    assert same[decided].all()
+    np.testing.assert_allclose(total.cpu().numpy()[same], g["final_total_cost"][same], rtol=FINAL_COST_RTOL, atol=0)
+    tc = env.true_cost().cpu().numpy()
+    assert np.isfinite(tc).all()
 
 
 @pytest.mark.parametrize("name", ["g21_pomo", "g51_upd2"])
