@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--instances", type=int, default=4096, help="instances per GPU (config 2: 4096)")
-    ap.add_argument("--precision", default=os.environ.get("JAMPR_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("JAMPR_PRECISION", "bf16"), choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="instances of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -57,6 +57,13 @@ def flops_tour_encoder(N, H=128, D=256):
     """Algorithmic dense FLOPs of one tour-graph GNN refresh per rollout: node_emb_input_proj +
     6 GraphConv blocks (lin_rel + lin_root) + node_emb_output_proj."""
     return 2 * N * D * H + 12 * (2 * N * H * H) + 2 * N * H * D
+
+
+def flops_policy_step(N, A, K=3, H=128, D=256):
+    """Algorithmic dense FLOPs of one whole policy step per rollout, F_step(N, A) of SURVEY.md §8d (the reference's
+    formulation: set_proj applied to every action embedding) = 84.53 MFLOP at N=101, A=78."""
+    return (flops_tour_encoder(N, H, D) + K * (2 * 5 * H + 2 * 2 * H * D) + 2 * 2 * D * D + 2 * A * D * 3 * D
+            + 4 * A * D + 2 * D * D + 2 * A * D)
 
 
 class ClockSampler:
@@ -281,27 +288,34 @@ def main():
         evs = []
         cap = env.graph_size + env.max_vehicle_number + 1
         step = env._step
+        fused = args.precision != "fp32"      # tensor-core path: GNN + decoder are ONE kernel per step
         while step <= cap:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            _cabi.check(lib.jampr_tour_encoder(d, p, w, st.struct(), step, S), "jampr_tour_encoder")
+            if fused:
+                _cabi.check(lib.jampr_policy_step(d, p, w, st.struct(), 1, step, 0, 0, None, S), "jampr_policy_step")
+            else:
+                _cabi.check(lib.jampr_tour_encoder(d, p, w, st.struct(), step, S), "jampr_tour_encoder")
             b.record()
             evs.append((a, b))
-            _cabi.check(lib.jampr_policy_step(d, p, w, st.struct(), 0, step, 0, 0, None, S), "jampr_policy_step")
+            if not fused:
+                _cabi.check(lib.jampr_policy_step(d, p, w, st.struct(), 0, step, 0, 0, None, S), "jampr_policy_step")
             _cabi.check(lib.jampr_env_step(d, p, st.struct(), None, step, S), "jampr_env_step")
             step += 1
         torch.cuda.synchronize()
         done2 = int(st["ctl"][_cabi.CTL_DONE_STEP].item())
         live = [a.elapsed_time(b) for i, (a, b) in enumerate(evs) if env._step + i <= done2]
         avg_ms = float(np.mean(live))
-        fl = flops_tour_encoder(env.graph_size) * bs
+        A_act = ENV_KW["max_concurrent_vehicles"] * env.k_nbh_size
+        fl = (flops_policy_step(env.graph_size, A_act) if fused else flops_tour_encoder(env.graph_size)) * bs
         peaks = {}
         pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk_path):
             peaks = json.load(open(pk_path))
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = fl / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "tour_encoder", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+        roof = {"bound": "tensor", "kernel": "policy_step_tc (tour-graph GNN + decoder, fused)" if fused else "tour_encoder_f32",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                 "flops_per_launch": fl, "avg_launch_ms": avg_ms, "launches_timed": len(live),
@@ -313,7 +327,7 @@ def main():
         return
     n_it = done_step - ENV_KW["max_concurrent_vehicles"] + 1          # live iterations of the device loop
     enq = env.graph_size + env.max_vehicle_number + 1 - ENV_KW["max_concurrent_vehicles"] + 1
-    launches = args.steps * (3 + 4 * enq + 1)
+    launches = args.steps * (3 + (3 if args.precision != "fp32" else 4) * enq + 1)
     in_bytes = sum(v.numel() * 4 for v in pinned.values())
     out_bytes = out_cost.numel() * 4 + out_plan.numel() * 2
     total_rollouts = bs * world
@@ -321,7 +335,7 @@ def main():
         "metric": METRIC, "value": total_rollouts * args.steps / (ms_res * 1e-3), "unit": "rollouts/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic",
         "config": {"workload": "config2: batched POMO greedy rollouts, 4096 synthetic CVRPTW-100 instances (all_1_low-like) x 16 samples per GPU",
                    "instances_per_gpu": I, "num_samples": P, "rollouts_per_gpu": bs, "graph_size": GRAPH_SIZE + 1,
                    "weights": "seeded random init, out_proj x0.1 (shipped checkpoints absent from the reference mount)",

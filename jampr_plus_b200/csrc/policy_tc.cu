@@ -72,19 +72,54 @@ __device__ __forceinline__ uint16_t bits_T(float v) {
   return *reinterpret_cast<uint16_t*>(&t);
 }
 
-// erf to 1.5e-7 absolute (Abramowitz-Stegun 7.1.26) -> GELU(erf) well inside the 16-bit operand noise
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  p *= t;
-  const float e = __expf(-ax * ax);
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  const float hx = 0.5f * x;
-  return fmaf(copysignf(erf_abs, x), hx, hx);
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+
+// GELU(erf) on two values with the packed fp32 pipe (FFMA2 / FMUL2): erf to 1.5e-7 absolute
+// (Abramowitz-Stegun 7.1.26), well inside the 16-bit operand noise of this path.
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  float2 ax = __fmul2_rn(x, f2(0.70710678118654752f));
+  ax.x = fabsf(ax.x);
+  ax.y = fabsf(ax.y);
+  const float2 dn = __ffma2_rn(ax, f2(0.3275911f), f2(1.0f));
+  const float2 t = make_float2(rcp_approx(dn.x), rcp_approx(dn.y));
+  float2 p = __ffma2_rn(t, f2(-1.061405429f), f2(1.453152027f));      // coefficients negated: p = -poly
+  p = __ffma2_rn(t, p, f2(-1.421413741f));
+  p = __ffma2_rn(t, p, f2(0.284496736f));
+  p = __ffma2_rn(t, p, f2(-0.254829592f));
+  p = __fmul2_rn(p, t);
+  float2 z = __fmul2_rn(ax, ax);
+  z = __fmul2_rn(z, f2(-1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(z.x), ex2_approx(z.y));
+  const float2 ea = __ffma2_rn(p, e, f2(1.0f));                        // erf(|x| / sqrt 2)
+  const float2 hx = __fmul2_rn(x, f2(0.5f));
+  const float2 sg = make_float2(copysignf(ea.x, x.x), copysignf(ea.y, x.y));
+  return __ffma2_rn(sg, hx, hx);
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
 }
 
 // ---- one K-block (64 of K) of a 128 x 128 tile product: 4 tcgen05.mma of K = 16
@@ -101,115 +136,122 @@ __device__ __forceinline__ void load_w_stage(uint8_t* sW, int stage, const void*
            16384u, &full[stage]);
 }
 
-// ---- max aggregation over the static neighbourhood graph into the agg tiles (K-blocks 0,1), packed 16-bit math.
-// tid < 16: the depot row (receives from every node, weight = time to depot); the other 496 threads: 31 customers
-// at a time, 16 threads (16-byte chunks of the 128 features) per customer.
+// ---- max aggregation into the agg tiles (K-blocks 0,1), packed 16-bit math.
+// An edge is one 32-bit table entry: low half = byte offset of the source row inside an h tile with the row's
+// swizzle phase folded in (row * 128 | (row & 7) << 4), high half = the edge weight in the operand type.  The
+// 16-byte chunk c of that row then sits at (entry & 0xffff) ^ (c << 4).  Rows are padded to a multiple of four
+// entries by repeating the last edge (max is idempotent), so the table is read with 128-bit loads.
+__device__ __forceinline__ uint32_t agg_entry(uint32_t row, uint16_t wbits) {
+  return (row << 7) | ((row & 7u) << 4) | ((uint32_t)wbits << 16);
+}
+
 template <typename T>
-__device__ __forceinline__ void agg_nbh_tc(uint8_t* sA, const uint32_t* s_tab, const T* s_ttd, int N, int k) {
+__device__ __forceinline__ void agg_edge(uint32_t e, uint32_t hb, uint32_t c4, typename Elem<T>::T2 (&m)[4], bool first) {
+  using T2 = typename Elem<T>::T2;
+  const T2 w2 = from_u32<T2>(__byte_perm(e, e, 0x3232));
+  const uint4 v = lds128(hb + ((e & 0xffffu) ^ c4));
+  const T2 p0 = __hmul2(from_u32<T2>(v.x), w2), p1 = __hmul2(from_u32<T2>(v.y), w2);
+  const T2 p2 = __hmul2(from_u32<T2>(v.z), w2), p3 = __hmul2(from_u32<T2>(v.w), w2);
+  if (first) { m[0] = p0; m[1] = p1; m[2] = p2; m[3] = p3; }
+  else { m[0] = __hmax2(m[0], p0); m[1] = __hmax2(m[1], p1); m[2] = __hmax2(m[2], p2); m[3] = __hmax2(m[3], p3); }
+}
+
+// max over entries [e0, e1) (both multiples of 4, e1 > e0) of weight * h[source] for one 16-byte chunk
+template <typename T>
+__device__ __forceinline__ uint4 agg_run(uint32_t tab_saddr, int e0, int e1, uint32_t hb, uint32_t c4) {
+  using T2 = typename Elem<T>::T2;
+  T2 m[4];
+  for (int j = e0; j < e1; j += 4) {
+    const uint4 q = lds128(tab_saddr + (uint32_t)j * 4u);
+    agg_edge<T>(q.x, hb, c4, m, j == e0);
+    agg_edge<T>(q.y, hb, c4, m, false);
+    agg_edge<T>(q.z, hb, c4, m, false);
+    agg_edge<T>(q.w, hb, c4, m, false);
+  }
+  return make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
+}
+
+// Static neighbourhood graph (graph_utils.py:127-141).  Warp 0: the depot row (receives from every node, weight =
+// time to depot), node range split over the two half-warps; warps 1..15: 30 customers at a time, 16 threads
+// (16-byte chunks of the 128 features) per customer.
+template <typename T>
+__device__ __forceinline__ void agg_nbh_tc(uint8_t* sA, uint32_t tab_saddr, int k4, uint32_t dtab_saddr, int nd, int N) {
   using T2 = typename Elem<T>::T2;
   const int tid = threadIdx.x;
-  const uint8_t* sH = sA + 2 * 16384;
-  if (tid < 16) {
-    const uint32_t kboff = (uint32_t)(tid >> 3) * 16384u, c = tid & 7;
-    T2 m[4];
-    for (int u = 0; u < N; ++u) {
-      const uint4 v = *reinterpret_cast<const uint4*>(sH + kboff + sw128_off(u, c));
-      T2 w2;
-      w2.x = s_ttd[u];
-      w2.y = s_ttd[u];
-      const T2 p0 = __hmul2(from_u32<T2>(v.x), w2), p1 = __hmul2(from_u32<T2>(v.y), w2);
-      const T2 p2 = __hmul2(from_u32<T2>(v.z), w2), p3 = __hmul2(from_u32<T2>(v.w), w2);
-      if (u == 0) { m[0] = p0; m[1] = p1; m[2] = p2; m[3] = p3; }
-      else { m[0] = __hmax2(m[0], p0); m[1] = __hmax2(m[1], p1); m[2] = __hmax2(m[2], p2); m[3] = __hmax2(m[3], p3); }
-    }
-    *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
-  } else {
-    const int g = (tid - 16) >> 4, cc = (tid - 16) & 15;
+  const uint32_t h_saddr = smem_u32(sA) + 2u * 16384u;
+  if (tid < 32) {
+    const int cc = tid & 15, half = tid >> 4;
     const uint32_t kboff = (uint32_t)(cc >> 3) * 16384u, c = cc & 7;
-    for (int u = 1 + g; u < N; u += 31) {
-      const uint32_t* tb = s_tab + u * k;
+    uint4 r = agg_run<T>(dtab_saddr, half * (nd >> 1), (half + 1) * (nd >> 1), h_saddr + kboff, c << 4);
+    r.x = as_u32(__hmax2(from_u32<T2>(r.x), from_u32<T2>(__shfl_xor_sync(0xffffffffu, r.x, 16))));
+    r.y = as_u32(__hmax2(from_u32<T2>(r.y), from_u32<T2>(__shfl_xor_sync(0xffffffffu, r.y, 16))));
+    r.z = as_u32(__hmax2(from_u32<T2>(r.z), from_u32<T2>(__shfl_xor_sync(0xffffffffu, r.z, 16))));
+    r.w = as_u32(__hmax2(from_u32<T2>(r.w), from_u32<T2>(__shfl_xor_sync(0xffffffffu, r.w, 16))));
+    if (half == 0) *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = r;
+  } else {
+    const int g = (tid - 32) >> 4, cc = (tid - 32) & 15;
+    const uint32_t kboff = (uint32_t)(cc >> 3) * 16384u, c = cc & 7;
+    for (int u = 1 + g; u < N; u += 30) {
+      const uint4 r = agg_run<T>(tab_saddr + (uint32_t)(u * k4) * 4u, 0, k4, h_saddr + kboff, c << 4);
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, c)) = r;
+    }
+  }
+}
+
+// Tour graph (env.py:804-835): customer u receives from its predecessor (successor in the reversed graph) when it
+// is on a tour — ltab[u] is that single edge, or the zero-weight edge 0 otherwise; the depot receives from the
+// tour ends (etab, n_e4 entries padded to a multiple of 4, 0 = no tour yet -> zeros).
+template <typename T>
+__device__ __forceinline__ void agg_tour_tc(uint8_t* sA, const uint32_t* s_ltab, uint32_t etab_saddr, int n_e4, int N) {
+  using T2 = typename Elem<T>::T2;
+  const int tid = threadIdx.x;
+  const uint32_t h_saddr = smem_u32(sA) + 2u * 16384u;
+  if (tid < 32) {
+    if (tid < 16) {
+      const uint32_t kboff = (uint32_t)(tid >> 3) * 16384u, c = tid & 7;
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      if (n_e4 > 0) r = agg_run<T>(etab_saddr, 0, n_e4, h_saddr + kboff, c << 4);
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = r;
+    }
+  } else {
+    const int g = (tid - 32) >> 4, cc = (tid - 32) & 15;
+    const uint32_t kboff = (uint32_t)(cc >> 3) * 16384u, c = cc & 7;
+    for (int u = 1 + g; u < N; u += 30) {
       T2 m[4];
-#pragma unroll 2
-      for (int j = 0; j < k; ++j) {
-        const uint32_t e = tb[j];
-        const uint32_t nb = e & 0xffffu;
-        const T2 w2 = from_u32<T2>(__byte_perm(e, e, 0x3232));
-        const uint4 v = *reinterpret_cast<const uint4*>(sH + kboff + nb * 128u + ((c ^ (nb & 7u)) << 4));
-        const T2 p0 = __hmul2(from_u32<T2>(v.x), w2), p1 = __hmul2(from_u32<T2>(v.y), w2);
-        const T2 p2 = __hmul2(from_u32<T2>(v.z), w2), p3 = __hmul2(from_u32<T2>(v.w), w2);
-        if (j == 0) { m[0] = p0; m[1] = p1; m[2] = p2; m[3] = p3; }
-        else { m[0] = __hmax2(m[0], p0); m[1] = __hmax2(m[1], p1); m[2] = __hmax2(m[2], p2); m[3] = __hmax2(m[3], p3); }
-      }
+      agg_edge<T>(s_ltab[u], h_saddr + kboff, c << 4, m, true);
       *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, c)) = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
     }
   }
 }
 
-// ---- max aggregation over the tour graph (env.py:804-835): customer u receives from link[u] (its predecessor, or
-// successor in the reversed graph) if it is on a tour, nothing otherwise; the depot receives from the tour ends.
-template <typename T>
-__device__ __forceinline__ void agg_tour_tc(uint8_t* sA, const uint8_t* s_vis, const int16_t* s_link, const T* s_wlink,
-                                            const int16_t* s_ends, int n_ends, const T* s_ttd, int N) {
-  using T2 = typename Elem<T>::T2;
-  const int tid = threadIdx.x;
-  const uint8_t* sH = sA + 2 * 16384;
-  if (tid < 16) {
-    const uint32_t kboff = (uint32_t)(tid >> 3) * 16384u, c = tid & 7;
-    T2 m[4];
-    m[0] = m[1] = m[2] = m[3] = Elem<T>::bcast(0.0f);
-    for (int i = 0; i < n_ends; ++i) {
-      const int u = s_ends[i];
-      const uint4 v = *reinterpret_cast<const uint4*>(sH + kboff + sw128_off(u, c));
-      T2 w2;
-      w2.x = s_ttd[u];
-      w2.y = s_ttd[u];
-      const T2 p0 = __hmul2(from_u32<T2>(v.x), w2), p1 = __hmul2(from_u32<T2>(v.y), w2);
-      const T2 p2 = __hmul2(from_u32<T2>(v.z), w2), p3 = __hmul2(from_u32<T2>(v.w), w2);
-      if (i == 0) { m[0] = p0; m[1] = p1; m[2] = p2; m[3] = p3; }
-      else { m[0] = __hmax2(m[0], p0); m[1] = __hmax2(m[1], p1); m[2] = __hmax2(m[2], p2); m[3] = __hmax2(m[3], p3); }
-    }
-    *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
-  } else {
-    const int g = (tid - 16) >> 4, cc = (tid - 16) & 15;
-    const uint32_t kboff = (uint32_t)(cc >> 3) * 16384u, c = cc & 7;
-    for (int u = 1 + g; u < N; u += 31) {
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (s_vis[u]) {
-        const uint32_t nb = (uint32_t)s_link[u];
-        T2 w2;
-        w2.x = s_wlink[u];
-        w2.y = s_wlink[u];
-        const uint4 v = *reinterpret_cast<const uint4*>(sH + kboff + nb * 128u + ((c ^ (nb & 7u)) << 4));
-        o = make_uint4(as_u32(__hmul2(from_u32<T2>(v.x), w2)), as_u32(__hmul2(from_u32<T2>(v.y), w2)),
-                       as_u32(__hmul2(from_u32<T2>(v.z), w2)), as_u32(__hmul2(from_u32<T2>(v.w), w2)));
-      }
-      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, c)) = o;
-    }
-  }
-}
-
 // ---- layer epilogue: y = GELU(acc + b) + skip -> LayerNorm -> new h (fp32 into the TMEM skip columns, 16-bit into
-// the h tiles, optionally fp32 to HBM).  Thread (q, lane, cg): row 32q+lane, columns 32cg..32cg+31.
+// the h tiles, optionally fp32 to HBM).  Thread (q, lane, cg): row 32q+lane, columns 32cg..32cg+31.  par_saddr:
+// shared address of this layer's [bias 128 | gamma 128 | beta 128]; all math on the packed fp32 pipe.
 template <typename T>
-__device__ __forceinline__ void layer_epilogue(uint32_t tmem, uint8_t* sA, float2* s_red, const float* __restrict__ blk,
-                                               int N, float* __restrict__ hfin) {
-  using T2 = typename Elem<T>::T2;
+__device__ __forceinline__ void layer_epilogue(uint32_t tmem, uint8_t* sA, float2* s_red, uint32_t par_saddr, int N,
+                                               float* __restrict__ hfin) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, cg = warp >> 2, r = q * 32 + lane;
   const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16);
   uint32_t acc[32], sk[32];
   tmem_ld32_nowait(ta + cg * 32, acc);
   tmem_ld32_nowait(ta + 128 + cg * 32, sk);
   tmem_wait_ld();
-  float s = 0.0f, qq = 0.0f;
+  float2 s2 = make_float2(0.0f, 0.0f), q2 = make_float2(0.0f, 0.0f);
+  const uint32_t pb = par_saddr + (uint32_t)cg * 128u;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float x = __uint_as_float(acc[j]) + __ldg(blk + BLK_B + cg * 32 + j);
-    const float y = gelu_fast(x) + __uint_as_float(sk[j]);
-    acc[j] = __float_as_uint(y);
-    s += y;
-    qq = fmaf(y, y, qq);
+  for (int i = 0; i < 8; ++i) {
+    const float4 b4 = lds_f32x4(pb + i * 16);
+    float2 y0 = gelu2(__fadd2_rn(make_float2(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1])), make_float2(b4.x, b4.y)));
+    float2 y1 = gelu2(__fadd2_rn(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), make_float2(b4.z, b4.w)));
+    y0 = __fadd2_rn(y0, make_float2(__uint_as_float(sk[4 * i]), __uint_as_float(sk[4 * i + 1])));
+    y1 = __fadd2_rn(y1, make_float2(__uint_as_float(sk[4 * i + 2]), __uint_as_float(sk[4 * i + 3])));
+    s2 = __fadd2_rn(s2, __fadd2_rn(y0, y1));
+    q2 = __ffma2_rn(y0, y0, q2);
+    q2 = __ffma2_rn(y1, y1, q2);
+    acc[4 * i] = __float_as_uint(y0.x); acc[4 * i + 1] = __float_as_uint(y0.y);
+    acc[4 * i + 2] = __float_as_uint(y1.x); acc[4 * i + 3] = __float_as_uint(y1.y);
   }
-  s_red[cg * 128 + r] = make_float2(s, qq);
+  s_red[cg * 128 + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
   __syncthreads();
   float ts = 0.0f, tq = 0.0f;
 #pragma unroll
@@ -220,12 +262,16 @@ __device__ __forceinline__ void layer_epilogue(uint32_t tmem, uint8_t* sA, float
   }
   const float mean = ts * (1.0f / 128.0f);
   const float var = fmaxf(fmaf(-mean, mean, tq * (1.0f / 128.0f)), 0.0f);
-  const float rstd = rsqrtf(var + 1e-5f);
+  const float2 rstd2 = f2(rsqrtf(var + 1e-5f)), nmean2 = f2(-mean);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int c = cg * 32 + j;
-    const float o = (__uint_as_float(acc[j]) - mean) * rstd * __ldg(blk + BLK_G + c) + __ldg(blk + BLK_BETA + c);
-    acc[j] = __float_as_uint(o);
+  for (int i = 0; i < 8; ++i) {
+    const float4 g4 = lds_f32x4(pb + 512 + i * 16), e4 = lds_f32x4(pb + 1024 + i * 16);
+    const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1])), nmean2);
+    const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), nmean2);
+    const float2 o0 = __ffma2_rn(d0, __fmul2_rn(make_float2(g4.x, g4.y), rstd2), make_float2(e4.x, e4.y));
+    const float2 o1 = __ffma2_rn(d1, __fmul2_rn(make_float2(g4.z, g4.w), rstd2), make_float2(e4.z, e4.w));
+    acc[4 * i] = __float_as_uint(o0.x); acc[4 * i + 1] = __float_as_uint(o0.y);
+    acc[4 * i + 2] = __float_as_uint(o1.x); acc[4 * i + 3] = __float_as_uint(o1.y);
   }
   tmem_st32(ta + 128 + cg * 32, acc);
   if (r < N) {
@@ -251,8 +297,9 @@ __device__ __forceinline__ void layer_epilogue(uint32_t tmem, uint8_t* sA, float
 
 // ---- decoder mat-vec partials: y[o] = sum_c x[c] W[c][o] over 256 outputs, W 16-bit [K][256].  A thread owns OPT
 // adjacent outputs and one of 512*OPT/256 K-slices; partial sums go to s_part[(slice * NV + v) * 256 + o].
+// x_saddr: shared address of this thread's input vector(s), vector v at + v * xstride floats.
 template <typename T, int OPT, int NV>
-__device__ __forceinline__ void matvec_partial(const T* __restrict__ W, int K, const float* x, int xstride, float* s_part) {
+__device__ __forceinline__ void matvec_partial(const T* __restrict__ W, int K, uint32_t x_saddr, int xstride, float* s_part) {
   using T2 = typename Elem<T>::T2;
   constexpr int NG = 256 / OPT, NS = PT_THREADS / NG;
   const int og = threadIdx.x % NG, ks = threadIdx.x / NG;
@@ -263,14 +310,15 @@ __device__ __forceinline__ void matvec_partial(const T* __restrict__ W, int K, c
 #pragma unroll
     for (int j = 0; j < OPT; ++j) acc[v][j] = 0.0f;
   const T* wp = W + (size_t)k0 * 256 + og * OPT;
-#pragma unroll 4
+  const uint32_t xa = x_saddr + (uint32_t)k0 * 4u;
+#pragma unroll 8
   for (int c = 0; c < kn; ++c) {
     float wv[OPT];
     if constexpr (OPT == 8) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)c * 256));
       const float2 f0 = Elem<T>::to2(from_u32<T2>(raw.x)), f1 = Elem<T>::to2(from_u32<T2>(raw.y));
-      const float2 f2 = Elem<T>::to2(from_u32<T2>(raw.z)), f3 = Elem<T>::to2(from_u32<T2>(raw.w));
-      wv[0] = f0.x; wv[1] = f0.y; wv[2] = f1.x; wv[3] = f1.y; wv[4] = f2.x; wv[5] = f2.y; wv[6] = f3.x; wv[7] = f3.y;
+      const float2 f2_ = Elem<T>::to2(from_u32<T2>(raw.z)), f3 = Elem<T>::to2(from_u32<T2>(raw.w));
+      wv[0] = f0.x; wv[1] = f0.y; wv[2] = f1.x; wv[3] = f1.y; wv[4] = f2_.x; wv[5] = f2_.y; wv[6] = f3.x; wv[7] = f3.y;
     } else {
       static_assert(OPT == 2, "OPT must be 8 or 2");
       const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(wp + (size_t)c * 256));
@@ -279,15 +327,35 @@ __device__ __forceinline__ void matvec_partial(const T* __restrict__ W, int K, c
     }
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      const float xv = x[v * xstride + k0 + c];
+      const float xv = lds_f32(xa + (uint32_t)(v * xstride + c) * 4u);
 #pragma unroll
-      for (int j = 0; j < OPT; ++j) acc[v][j] = fmaf(wv[j], xv, acc[v][j]);
+      for (int j = 0; j < OPT; j += 2) {
+        const float2 a2 = __ffma2_rn(make_float2(wv[j], wv[j + 1]), f2(xv), make_float2(acc[v][j], acc[v][j + 1]));
+        acc[v][j] = a2.x;
+        acc[v][j + 1] = a2.y;
+      }
     }
   }
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int j = 0; j < OPT; ++j) s_part[(ks * NV + v) * 256 + og * OPT + j] = acc[v][j];
+}
+
+// sum over the warp of four values at once: lane 16*(h>>1) + 8*(h&1) ends up with the total of value h
+__device__ __forceinline__ float warp_sum4(float d0, float d1, float d2, float d3, int lane) {
+  const bool up4 = (lane & 16) != 0, up3 = (lane & 8) != 0;
+  float x0 = up4 ? d2 : d0, x1 = up4 ? d3 : d1;
+  const float y0 = up4 ? d0 : d2, y1 = up4 ? d1 : d3;
+  x0 += __shfl_xor_sync(0xffffffffu, y0, 16);
+  x1 += __shfl_xor_sync(0xffffffffu, y1, 16);
+  float z = up3 ? x1 : x0;
+  const float sn = up3 ? x0 : x1;
+  z += __shfl_xor_sync(0xffffffffu, sn, 8);
+  z += __shfl_xor_sync(0xffffffffu, z, 4);
+  z += __shfl_xor_sync(0xffffffffu, z, 2);
+  z += __shfl_xor_sync(0xffffffffu, z, 1);
+  return z;
 }
 
 template <typename T>
@@ -300,56 +368,56 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   const int done_step = st.ctl[JAMPR_CTL_DONE_STEP];
   if (done_step >= 0 && done_step < a.step_no) return;
   const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh, A = K * k, L = d.plan_len;
+  const int k4 = (k + 3) & ~3, nd = (N + 7) & ~7;
   const int b = blockIdx.x, ins = b / d.n_samples;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ w = a.w;
   const T* __restrict__ w16 = reinterpret_cast<const T*>(a.w16);
   const bool fresh = a.graph_fresh != 0;
 
-  // ---------------------------------------------------------------- shared memory carve-up
+  // ---------------------------------------------------------------- shared memory carve-up (32-bit offsets)
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = base;               // 4 operand tiles: agg (K-blocks 0,1), h (K-blocks 2,3)
   uint8_t* sW = base + 65536;       // 4 weight stages
   float* s_ne = reinterpret_cast<float*>(base);   // node embedding rows, parked over sA/sW once the GNN is done
-  uint8_t* cur = base + OVERLAY_BYTES;
-  auto take = [&](size_t bytes) {
-    uint8_t* r = cur;
-    cur += (bytes + 15) & ~size_t(15);
+  uint32_t off = OVERLAY_BYTES;
+  auto take = [&](uint32_t bytes) {
+    uint8_t* r = base + off;
+    off += (bytes + 15u) & ~15u;
     return r;
   };
   uint64_t* bars = reinterpret_cast<uint64_t*>(take(64));     // full[0..3], root, acc
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(take(16));
   float2* s_red = reinterpret_cast<float2*>(take(4 * 128 * sizeof(float2)));
   float* s_part = reinterpret_cast<float*>(take(16 * 256 * 4));
-  uint32_t* s_tab = reinterpret_cast<uint32_t*>(take((size_t)N * k * 4));
-  T* s_ttd = reinterpret_cast<T*>(take(N * 2));
-  T* s_wpred = reinterpret_cast<T*>(take(N * 2));
-  T* s_wsucc = reinterpret_cast<T*>(take(N * 2));
-  int16_t* s_pred = reinterpret_cast<int16_t*>(take(N * 2));
-  int16_t* s_succ = reinterpret_cast<int16_t*>(take(N * 2));
-  int16_t* s_endf = reinterpret_cast<int16_t*>(take(N * 2));
-  int16_t* s_endr = reinterpret_cast<int16_t*>(take(N * 2));
-  uint8_t* s_vis = take(N);
+  float* s_par = reinterpret_cast<float*>(take(6 * 384 * 4));          // per layer: bias | gamma | beta
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(take((uint32_t)N * k4 * 4));
+  uint32_t* s_dtab = reinterpret_cast<uint32_t*>(take((uint32_t)nd * 4));
+  uint32_t* s_lf = reinterpret_cast<uint32_t*>(take((uint32_t)N * 4));
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(take((uint32_t)N * 4));
+  uint32_t* s_ef = reinterpret_cast<uint32_t*>(take((uint32_t)(N + 4) * 4));
+  uint32_t* s_er = reinterpret_cast<uint32_t*>(take((uint32_t)(N + 4) * 4));
   int* s_cnt = reinterpret_cast<int*>(take(16));
-  int16_t* s_plan = reinterpret_cast<int16_t*>(take((size_t)K * L * 2));
-  float* s_mean = reinterpret_cast<float*>(take((size_t)K * 128 * 4));
-  float* s_te = reinterpret_cast<float*>(take((size_t)K * 256 * 4));
+  int16_t* s_plan = reinterpret_cast<int16_t*>(take((uint32_t)K * L * 2));
+  float* s_mean = reinterpret_cast<float*>(take(4 * 128 * 4));
+  float* s_te = reinterpret_cast<float*>(take((uint32_t)K * 256 * 4));
   float* s_q = reinterpret_cast<float*>(take(512 * 4));
   float* s_ctxt = reinterpret_cast<float*>(take(256 * 4));
   float* s_qp = reinterpret_cast<float*>(take(4 * QP_STRIDE * 4));
   float* s_gbar = reinterpret_cast<float*>(take(4 * QP_STRIDE * 4));
   float* s_g = reinterpret_cast<float*>(take(256 * 4));
   float* s_lp = reinterpret_cast<float*>(take(256 * 4));
-  float* s_sn = reinterpret_cast<float*>(take(4 * 128 * 4));
+  float4* s_sn4 = reinterpret_cast<float4*>(take(128 * 16));           // per node: glimpse score of the 4 heads
   float* s_ln = reinterpret_cast<float*>(take(128 * 4));
-  float* s_pn = reinterpret_cast<float*>(take(4 * 128 * 4));
+  float4* s_pn4 = reinterpret_cast<float4*>(take(128 * 16));           // per node: glimpse weight of the 4 heads
   float* s_qt = reinterpret_cast<float*>(take(4 * JAMPR_MAX_SLOTS * 4));
   float* s_lt = reinterpret_cast<float*>(take(JAMPR_MAX_SLOTS * 4));
   float* s_P = reinterpret_cast<float*>(take(4 * JAMPR_MAX_SLOTS * 4));
-  float* s_sc = reinterpret_cast<float*>(take((size_t)4 * A * 4));
-  float* s_logit = reinterpret_cast<float*>(take((size_t)A * 4));
-  float* s_feat = reinterpret_cast<float*>(take((size_t)K * 8 * 4));
-  int* s_nbh = reinterpret_cast<int*>(take((size_t)A * 4));
+  float* s_sc = reinterpret_cast<float*>(take((uint32_t)4 * A * 4));
+  float* s_logit = reinterpret_cast<float*>(take((uint32_t)A * 4));
+  float* s_feat = reinterpret_cast<float*>(take((uint32_t)K * 8 * 4));
+  int* s_nbh = reinterpret_cast<int*>(take((uint32_t)A * 4));
+  int8_t* s_pos = reinterpret_cast<int8_t*>(take((uint32_t)K * N));    // slot t, node n -> candidate index j or -1
   uint8_t* s_mask = take(A);
   int* s_idx = reinterpret_cast<int*>(take(JAMPR_MAX_SLOTS * 4));
   uint64_t* full = bars;
@@ -369,8 +437,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
     if (warp == 0) tmem_alloc(tmem_slot, 256);
     // zero the operand tiles: rows >= N stay zero for the whole kernel
     for (int e = tid; e < 65536 / 16; e += PT_THREADS) reinterpret_cast<uint4*>(sA)[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = tid; e < 6 * 96; e += PT_THREADS) {
+      const int l = e / 96, i = e - l * 96;
+      reinterpret_cast<float4*>(s_par)[e] = __ldg(reinterpret_cast<const float4*>(w + OFF_TE_BLK + (size_t)l * BLK_FLOATS + BLK_B) + i);
+    }
   }
   if (tid < 4) s_cnt[tid] = 0;
+  for (int e = tid; e < K * N; e += PT_THREADS) s_pos[e] = (int8_t)-1;
   // tour features (env.py:1061-1068), tour buffer rows of the active vehicles and their lengths
   if (tid < K) {
     const size_t bk = (size_t)b * K + tid;
@@ -390,24 +463,28 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
     s_mask[e] = st.mask[(size_t)b * A + e];
   }
   __syncthreads();
+  for (int e = tid; e < A; e += PT_THREADS) s_pos[(e / k) * N + s_nbh[e]] = (int8_t)(e % k);
   if (fresh) {
     const int16_t* gk = p.knn + (size_t)ins * N * k;
     const float* gw = p.knn_w + (size_t)ins * N * k;
-    for (int e = tid; e < N * k; e += PT_THREADS)
-      s_tab[e] = (uint32_t)(uint16_t)gk[e] | ((uint32_t)bits_T<T>(gw[e]) << 16);
+    for (int e = tid; e < N * k4; e += PT_THREADS) {
+      const int u = e / k4, j = min(e - u * k4, k - 1);
+      s_tab[e] = agg_entry((uint32_t)(uint16_t)gk[u * k + j], bits_T<T>(gw[u * k + j]));
+    }
     const float* dist = p.dist + (size_t)ins * N * N;
+    for (int u = tid; u < nd; u += PT_THREADS) {
+      const int uu = min(u, N - 1);
+      s_dtab[u] = agg_entry((uint32_t)uu, bits_T<T>(p.ttd[(size_t)ins * N + uu]));
+    }
     for (int u = tid; u < N; u += PT_THREADS) {
       const int pr = st.pred[(size_t)b * N + u], su = st.succ[(size_t)b * N + u];
-      const int vs = st.visited[(size_t)b * N + u];
-      s_pred[u] = (int16_t)pr;
-      s_succ[u] = (int16_t)su;
-      s_vis[u] = (uint8_t)vs;
-      s_wpred[u] = to_T<T>(dist[(size_t)u * N + pr]);
-      s_wsucc[u] = to_T<T>(dist[(size_t)u * N + su]);
-      s_ttd[u] = to_T<T>(p.ttd[(size_t)ins * N + u]);
-      if (u > 0 && vs) {
-        if (su == 0) s_endf[atomicAdd(&s_cnt[0], 1)] = (int16_t)u;
-        if (pr == 0) s_endr[atomicAdd(&s_cnt[1], 1)] = (int16_t)u;
+      const bool vs = u > 0 && st.visited[(size_t)b * N + u] != 0;
+      s_lf[u] = vs ? agg_entry((uint32_t)pr, bits_T<T>(dist[(size_t)u * N + pr])) : 0u;
+      s_lr[u] = vs ? agg_entry((uint32_t)su, bits_T<T>(dist[(size_t)u * N + su])) : 0u;
+      if (vs) {
+        const uint32_t en = agg_entry((uint32_t)u, bits_T<T>(p.ttd[(size_t)ins * N + u]));
+        if (su == 0) s_ef[atomicAdd(&s_cnt[0], 1)] = en;
+        if (pr == 0) s_er[atomicAdd(&s_cnt[1], 1)] = en;
       }
     }
   }
@@ -427,6 +504,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
     const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16);
     const uint32_t idesc = umma_idesc(128, 128, Elem<T>::fmt);
     const uint32_t a_addr = smem_u32(sA), w_addr = smem_u32(sW);
+    // pad the tour-end tables to a multiple of four entries (repeat the last one)
+    const int n_endf = s_cnt[0], n_endr = s_cnt[1];
+    const int n_ef4 = (n_endf + 3) & ~3, n_er4 = (n_endr + 3) & ~3;
+    if (tid < 3 && n_endf > 0 && n_endf + tid < n_ef4) s_ef[n_endf + tid] = s_ef[n_endf - 1];
+    if (tid >= 32 && tid < 35 && n_endr > 0 && n_endr + (tid - 32) < n_er4) s_er[n_endr + tid - 32] = s_er[n_endr - 1];
     // ---- h_0 = node_emb_input_proj(static_emb) (hoisted, per instance): fp32 -> TMEM skip columns, 16-bit -> h tiles
     {
       uint32_t hv[32];
@@ -459,7 +541,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
     __syncthreads();
     tc_fence_after();
 
-    const int n_endf = s_cnt[0], n_endr = s_cnt[1];
+    const uint32_t tab_saddr = smem_u32(s_tab), dtab_saddr = smem_u32(s_dtab), par_saddr = smem_u32(s_par);
+    const uint32_t ef_saddr = smem_u32(s_ef), er_saddr = smem_u32(s_er);
     for (int l = 0; l < 6; ++l) {
       const uint32_t ph = (uint32_t)(l & 1);
       if (tid == 0) {
@@ -471,9 +554,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
         mma_kblock(tmem, a_addr + 3 * 16384, w_addr + 3 * 16384, idesc, false);
         umma_commit(bar_root);
       }
-      if (l == 2 || l == 5) agg_nbh_tc<T>(sA, s_tab, s_ttd, N, k);
-      else if (l < 2) agg_tour_tc<T>(sA, s_vis, s_pred, s_wpred, s_endf, n_endf, s_ttd, N);
-      else agg_tour_tc<T>(sA, s_vis, s_succ, s_wsucc, s_endr, n_endr, s_ttd, N);
+      if (l == 2 || l == 5) agg_nbh_tc<T>(sA, tab_saddr, k4, dtab_saddr, nd, N);
+      else if (l < 2) agg_tour_tc<T>(sA, s_lf, ef_saddr, n_ef4, N);
+      else agg_tour_tc<T>(sA, s_lr, er_saddr, n_er4, N);
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
@@ -493,7 +576,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
         load_w_stage<T>(sW, 0, a.w16, l + 1, full);
         load_w_stage<T>(sW, 1, a.w16, l + 1, full);
       }
-      layer_epilogue<T>(tmem, sA, s_red, w + OFF_TE_BLK + (size_t)l * BLK_FLOATS, N,
+      layer_epilogue<T>(tmem, sA, s_red, par_saddr + (uint32_t)l * 1536u, N,
                         (l == 5 && a.store_cache) ? st.h_fin + (size_t)b * N * 128 : nullptr);
       fence_proxy_async();
       tc_fence_before();
@@ -527,13 +610,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   // 0..idx (includes one depot entry, tour_encoder.py:236-243); overlaps the projection MMAs
   for (int e = tid; e < K * 64; e += PT_THREADS) {
     const int t = e >> 6, c2 = e & 63;              // feature pair 2*c2, 2*c2+1
-    const uint32_t off = (uint32_t)(2 + (c2 >> 5)) * 16384u;
+    const uint32_t toff = (uint32_t)(2 + (c2 >> 5)) * 16384u;
     const uint32_t ch = (uint32_t)(c2 & 31) >> 2, within = (uint32_t)(c2 & 3) * 4u;
     const int idx = s_idx[t];
     float sx = 0.0f, sy = 0.0f;
     for (int q = 0; q <= idx; ++q) {
       const uint32_t u = (uint32_t)s_plan[t * L + q];
-      const float2 v = Elem<T>::to2(*reinterpret_cast<const T2*>(sA + off + sw128_off(u, ch) + within));
+      const float2 v = Elem<T>::to2(*reinterpret_cast<const T2*>(sA + toff + sw128_off(u, ch) + within));
       sx += v.x;
       sy += v.y;
     }
@@ -549,12 +632,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
     const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16);
     mbar_wait(bar_acc, 0u);
     tc_fence_after();
-#pragma unroll 1
-    for (int hf = 0; hf < 2; ++hf) {
-      uint32_t acc[32];
-      tmem_ld32_nowait(ta + hf * 128 + cg * 32, acc);
-      tmem_wait_ld();
-      if (r < N) {
+    uint32_t acc0[32], acc1[32];
+    tmem_ld32_nowait(ta + cg * 32, acc0);
+    tmem_ld32_nowait(ta + 128 + cg * 32, acc1);
+    tmem_wait_ld();
+    if (r < N) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
         const int c0 = hf * 128 + cg * 32;
         const float4* se = reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + r) * 256 + c0);
         const float4* bo = reinterpret_cast<const float4*>(w + OFF_TE_OUT_B + c0);
@@ -563,8 +647,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 s4 = __ldg(se + i), b4 = __ldg(bo + i);
-          const float4 v = make_float4(__uint_as_float(acc[4 * i]) + b4.x + s4.x, __uint_as_float(acc[4 * i + 1]) + b4.y + s4.y,
-                                       __uint_as_float(acc[4 * i + 2]) + b4.z + s4.z, __uint_as_float(acc[4 * i + 3]) + b4.w + s4.w);
+          const uint32_t* ac = hf ? acc1 : acc0;
+          const float4 v = make_float4(__uint_as_float(ac[4 * i]) + b4.x + s4.x, __uint_as_float(ac[4 * i + 1]) + b4.y + s4.y,
+                                       __uint_as_float(ac[4 * i + 2]) + b4.z + s4.z, __uint_as_float(ac[4 * i + 3]) + b4.w + s4.w);
           dst[i] = v;
           if (gdst) gdst[i] = v;
         }
@@ -585,17 +670,27 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   }
 
   // ---------------------------------------------------------------- decoder
+  const uint32_t ne_saddr = smem_u32(s_ne), te_saddr = smem_u32(s_te);
   // (b) tour_emb[t] = folded tour-feature branch + W_to2 mean_h[t]          (tour_encoder.py:202-213)
-  matvec_partial<T, 2, 4>(w16 + W16_TO2, 128, s_mean, 128, s_part);   // NV = 4 >= K slots (K <= 4 on this path)
+  matvec_partial<T, 2, 4>(w16 + W16_TO2, 128, smem_u32(s_mean), 128, s_part);   // NV = 4 >= K slots (K <= 4 here)
   // (a) column mean / max of node_emb over the nodes (policy.py:179-181) — independent of (b)
   float nmean = 0.0f, nmax = -INFINITY;
   if (tid < 256) {
-    for (int u = 0; u < N; ++u) {
-      const float v = s_ne[(size_t)u * NE_STRIDE + tid];
-      nmean += v;
-      nmax = fmaxf(nmax, v);
+    float s0 = 0.0f, s1 = 0.0f, m0 = -INFINITY, m1 = -INFINITY;
+    int u = 0;
+    for (; u + 1 < N; u += 2) {
+      const float v0 = lds_f32(ne_saddr + (uint32_t)(u * NE_STRIDE + tid) * 4u);
+      const float v1 = lds_f32(ne_saddr + (uint32_t)((u + 1) * NE_STRIDE + tid) * 4u);
+      s0 += v0; s1 += v1;
+      m0 = fmaxf(m0, v0); m1 = fmaxf(m1, v1);
     }
-    nmean /= (float)N;
+    if (u < N) {
+      const float v0 = lds_f32(ne_saddr + (uint32_t)(u * NE_STRIDE + tid) * 4u);
+      s0 += v0;
+      m0 = fmaxf(m0, v0);
+    }
+    nmean = (s0 + s1) / (float)N;
+    nmax = fmaxf(m0, m1);
     if (a.store_cache && fresh) {
       st.ne_stats[(size_t)b * 512 + tid] = nmean;
       st.ne_stats[(size_t)b * 512 + 256 + tid] = nmax;
@@ -619,7 +714,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   }
   __syncthreads();
   // (c) ctxt = ctxt_proj(query)
-  matvec_partial<T, 8, 1>(w16 + W16_CTXT, 512, s_q, 0, s_part);
+  matvec_partial<T, 8, 1>(w16 + W16_CTXT, 512, smem_u32(s_q), 0, s_part);
   __syncthreads();
   if (tid < 256) {
     float v = 0.0f;
@@ -629,7 +724,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   }
   __syncthreads();
   // (d) qp[h] = W_gk,h^T ctxt_h : K-slice ks (16 rows of set_proj) belongs to head ks / 4
-  matvec_partial<T, 8, 1>(w16 + W16_GK, 256, s_ctxt, 0, s_part);
+  matvec_partial<T, 8, 1>(w16 + W16_GK, 256, smem_u32(s_ctxt), 0, s_part);
   __syncthreads();
   for (int e = tid; e < 1024; e += PT_THREADS) {
     const int h = e >> 8, c = e & 255;
@@ -637,30 +732,38 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
                               s_part[(4 * h + 3) * 256 + c];
   }
   __syncthreads();
-  // (e) per-node and per-tour glimpse scores qp_h . node_emb[n], qp_h . tour_emb[t]
-  for (int n = warp; n < N + K; n += PT_THREADS / 32) {
-    const float* row = (n < N) ? (s_ne + (size_t)n * NE_STRIDE) : (s_te + (n - N) * 256);
-    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+  // (e) per-node and per-tour glimpse scores qp_h . node_emb[n], qp_h . tour_emb[t]: one warp per row, the lane's
+  // eight columns of the four query vectors stay in registers
+  {
+    float qv[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = lane + 32 * i;
-      const float v = row[c];
-      d0 = fmaf(v, s_qp[c], d0);
-      d1 = fmaf(v, s_qp[QP_STRIDE + c], d1);
-      d2 = fmaf(v, s_qp[2 * QP_STRIDE + c], d2);
-      d3 = fmaf(v, s_qp[3 * QP_STRIDE + c], d3);
-    }
-    d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
-    if (lane == 0) {
-      if (n < N) { s_sn[n] = d0; s_sn[128 + n] = d1; s_sn[256 + n] = d2; s_sn[384 + n] = d3; }
-      else { const int t = n - N; s_qt[t] = d0; s_qt[8 + t] = d1; s_qt[16 + t] = d2; s_qt[24 + t] = d3; }
+    for (int h = 0; h < 4; ++h)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qv[h][i] = s_qp[h * QP_STRIDE + lane + 32 * i];
+    for (int n = warp; n < N + K; n += PT_THREADS / 32) {
+      const uint32_t ra = ((n < N) ? (ne_saddr + (uint32_t)n * NE_STRIDE * 4u) : (te_saddr + (uint32_t)(n - N) * 1024u)) + lane * 4u;
+      float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v = lds_f32(ra + i * 128u);
+        d0 = fmaf(v, qv[0][i], d0);
+        d1 = fmaf(v, qv[1][i], d1);
+        d2 = fmaf(v, qv[2][i], d2);
+        d3 = fmaf(v, qv[3][i], d3);
+      }
+      const float z = warp_sum4(d0, d1, d2, d3, lane);
+      if ((lane & 7) == 0) {
+        const int h = ((lane >> 4) << 1) | ((lane >> 3) & 1);
+        if (n < N) reinterpret_cast<float*>(s_sn4)[n * 4 + h] = z;
+        else s_qt[h * 8 + (n - N)] = z;
+      }
     }
   }
   __syncthreads();
   // (f) glimpse scores per action, softmax per head
   for (int e = tid; e < 4 * A; e += PT_THREADS) {
     const int h = e / A, aa = e - h * A;
-    const float sc = (s_sn[h * 128 + s_nbh[aa]] + s_qt[h * 8 + aa / k]) * 0.125f;
+    const float sc = (reinterpret_cast<const float*>(s_sn4)[s_nbh[aa] * 4 + h] + s_qt[h * 8 + aa / k]) * 0.125f;
     s_sc[e] = s_mask[aa] ? -INFINITY : sc;
   }
   __syncthreads();
@@ -679,16 +782,18 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
     for (int e = lane; e < A; e += 32) sc[e] = sc[e] / sum;
   }
   __syncthreads();
-  // glimpse weights folded onto nodes and tours (fixed summation order: deterministic)
+  // glimpse weights folded onto nodes and tours (fixed summation order over the slots: deterministic)
   for (int e = tid; e < 4 * N; e += PT_THREADS) {
-    const int h = e / N, n = e - h * N;
+    const int n = e >> 2, h = e & 3;
     float acc = 0.0f;
-    for (int aa = 0; aa < A; ++aa)
-      if (s_nbh[aa] == n) acc += s_sc[h * A + aa];
-    s_pn[h * 128 + n] = acc;
+    for (int t = 0; t < K; ++t) {
+      const int j = s_pos[t * N + n];
+      if (j >= 0) acc += s_sc[h * A + t * k + j];
+    }
+    reinterpret_cast<float*>(s_pn4)[e] = acc;
   }
-  if (tid < 4 * K) {
-    const int h = tid / K, t = tid - h * K;
+  if (tid >= 480 && tid < 480 + 4 * K) {
+    const int e = tid - 480, h = e / K, t = e - h * K;
     float acc = 0.0f;
     for (int j = 0; j < k; ++j) acc += s_sc[h * A + t * k + j];
     s_P[h * 8 + t] = acc;
@@ -697,13 +802,15 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   // (g) gbar[h] = sum_a p[h][a] act[a] = sum_t P[h][t] tour_emb[t] + sum_n pn[h][n] node_emb[n]
   {
     const int c = tid & 255, half = tid >> 8;
+    const uint32_t pn_saddr = smem_u32(s_pn4);
     float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
     for (int n = half; n < N; n += 2) {
-      const float v = s_ne[(size_t)n * NE_STRIDE + c];
-      g0 = fmaf(s_pn[n], v, g0);
-      g1 = fmaf(s_pn[128 + n], v, g1);
-      g2 = fmaf(s_pn[256 + n], v, g2);
-      g3 = fmaf(s_pn[384 + n], v, g3);
+      const float v = lds_f32(ne_saddr + (uint32_t)(n * NE_STRIDE + c) * 4u);
+      const float4 pw = lds_f32x4(pn_saddr + (uint32_t)n * 16u);
+      g0 = fmaf(pw.x, v, g0);
+      g1 = fmaf(pw.y, v, g1);
+      g2 = fmaf(pw.z, v, g2);
+      g3 = fmaf(pw.w, v, g3);
     }
     if (half == 0) {
       for (int t = 0; t < K; ++t) {
@@ -726,7 +833,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   }
   __syncthreads();
   // (h) glimpse g[o] = W_gv[o] . gbar[head(o)]
-  matvec_partial<T, 8, 1>(w16 + W16_GV, 256, s_gbar + ((tid & 31) >> 3) * QP_STRIDE, 0, s_part);
+  matvec_partial<T, 8, 1>(w16 + W16_GV, 256, smem_u32(s_gbar) + (uint32_t)((tid & 31) >> 3) * QP_STRIDE * 4u, 0, s_part);
   __syncthreads();
   if (tid < 256) {
     float v = 0.0f;
@@ -736,7 +843,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   }
   __syncthreads();
   // (i) lp = W_lk^T out_proj(g) = M1 g
-  matvec_partial<T, 8, 1>(w16 + W16_M1, 256, s_g, 0, s_part);
+  matvec_partial<T, 8, 1>(w16 + W16_M1, 256, smem_u32(s_g), 0, s_part);
   __syncthreads();
   if (tid < 256) {
     float v = 0.0f;
@@ -746,18 +853,20 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   }
   __syncthreads();
   // (j) pointer logits: 10 tanh((lp . node_emb[n] + lp . tour_emb[t]) / 16)
-  for (int n = warp; n < N + K; n += PT_THREADS / 32) {
-    const float* row = (n < N) ? (s_ne + (size_t)n * NE_STRIDE) : (s_te + (n - N) * 256);
-    float dd = 0.0f;
+  {
+    float lv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = lane + 32 * i;
-      dd = fmaf(row[c], s_lp[c], dd);
-    }
-    dd = warp_sum(dd);
-    if (lane == 0) {
-      if (n < N) s_ln[n] = dd;
-      else s_lt[n - N] = dd;
+    for (int i = 0; i < 8; ++i) lv[i] = s_lp[lane + 32 * i];
+    for (int n = warp; n < N + K; n += PT_THREADS / 32) {
+      const uint32_t ra = ((n < N) ? (ne_saddr + (uint32_t)n * NE_STRIDE * 4u) : (te_saddr + (uint32_t)(n - N) * 1024u)) + lane * 4u;
+      float dd = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dd = fmaf(lds_f32(ra + i * 128u), lv[i], dd);
+      dd = warp_sum(dd);
+      if (lane == 0) {
+        if (n < N) s_ln[n] = dd;
+        else s_lt[n - N] = dd;
+      }
     }
   }
   __syncthreads();
@@ -833,13 +942,15 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
 
 static size_t pt_smem_bytes(const jampr_dims_t* d) {
   const size_t N = d->n_nodes, k = d->k_nbh, K = d->n_slots, A = K * k, L = d->plan_len;
+  const size_t k4 = (k + 3) & ~size_t(3), nd = (N + 7) & ~size_t(7);
   auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
-  size_t s = 1024 + OVERLAY_BYTES;
-  s += al(64) + al(16) + al(4 * 128 * 8) + al(16 * 256 * 4) + al(N * k * 4);
-  s += 7 * al(N * 2) + al(N) + al(16) + al(K * L * 2) + al(K * 128 * 4) + al(K * 256 * 4) + al(512 * 4) + al(256 * 4);
-  s += 2 * al(4 * QP_STRIDE * 4) + 2 * al(256 * 4) + al(4 * 128 * 4) + al(128 * 4) + al(4 * 128 * 4);
-  s += al(4 * JAMPR_MAX_SLOTS * 4) + al(JAMPR_MAX_SLOTS * 4) + al(4 * JAMPR_MAX_SLOTS * 4) + al(4 * A * 4) + al(A * 4);
-  s += al(K * 8 * 4) + al(A * 4) + al(A) + al(JAMPR_MAX_SLOTS * 4);
+  size_t s = 1024 + OVERLAY_BYTES;   // alignment slack + operand tiles / weight stages / parked node embedding
+  s += al(64) + al(16) + al(4 * 128 * 8) + al(16 * 256 * 4) + al(6 * 384 * 4);          // bars, tmem slot, s_red, s_part, s_par
+  s += al(N * k4 * 4) + al(nd * 4) + 2 * al(N * 4) + 2 * al((N + 4) * 4) + al(16);       // edge tables, counters
+  s += al(K * L * 2) + al(4 * 128 * 4) + al(K * 256 * 4) + al(512 * 4) + al(256 * 4);    // plan, mean, te, q, ctxt
+  s += 2 * al(4 * QP_STRIDE * 4) + 2 * al(256 * 4) + al(128 * 16) + al(128 * 4) + al(128 * 16);   // qp, gbar, g, lp, sn4, ln, pn4
+  s += al(4 * JAMPR_MAX_SLOTS * 4) + al(JAMPR_MAX_SLOTS * 4) + al(4 * JAMPR_MAX_SLOTS * 4);       // qt, lt, P
+  s += al(4 * A * 4) + al(A * 4) + al(K * 8 * 4) + al(A * 4) + al(K * N) + al(A) + al(JAMPR_MAX_SLOTS * 4);
   return s;
 }
 
@@ -856,7 +967,7 @@ static int launch_pt(const PtArgs& a, size_t smem, cudaStream_t s) {
 int jampr_policy_step_tc(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
                          const jampr_state_t* st, int graph_fresh, int step_no, int decode_type, uint64_t seed,
                          const float* uniforms, int store_cache, cudaStream_t s) {
-  if (d->n_nodes > 128 || d->n_slots > 4 || d->k_nbh > 255) return JAMPR_E_TOOLARGE;
+  if (d->n_nodes > 128 || d->n_slots > 4 || d->k_nbh > 127) return JAMPR_E_TOOLARGE;
   if (!w->blob_bf16 || w->n_bf16 < (int64_t)W16_END) return JAMPR_E_BADARG;
   const size_t smem = pt_smem_bytes(d);
   if (smem > 227 * 1024) return JAMPR_E_TOOLARGE;
