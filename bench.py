@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--instances", type=int, default=4096, help="instances per GPU (config 2: 4096)")
-    ap.add_argument("--precision", default=os.environ.get("JAMPR_PRECISION", "bf16"), choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--precision", default=os.environ.get("JAMPR_PRECISION", "fp16"), choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="instances of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -224,12 +224,19 @@ def main():
         iters["n"] = env.graph_size + env.max_vehicle_number + 1 - ENV_KW["max_concurrent_vehicles"] + 1
         return env.gather_best()
 
-    out_cost = torch.empty(I, dtype=torch.float32).pin_memory()
+    out_cost = torch.empty(I * world if rank == 0 else I, dtype=torch.float32).pin_memory()
     out_plan = None
+
+    from jampr_plus_b200.sharding import gather_best
 
     def e2e_step():
         nonlocal out_plan
         cost, idx, plan = hot_path(pinned)
+        if world > 1:      # the one data-path collective: best tours of every shard, global instance order (NCCL)
+            cost, idx, plan = gather_best(cost, idx, plan, I * world)
+            if rank != 0:
+                torch.cuda.current_stream().synchronize()
+                return 0.0
         if out_plan is None:
             out_plan = torch.empty(plan.shape, dtype=plan.dtype).pin_memory()
         out_cost.copy_(cost, non_blocking=True)
@@ -343,7 +350,7 @@ def main():
                    "l2": "per-step working set (>= 10 GB of rollout state) exceeds the 126 MB L2; no explicit flush",
                    "precision": args.precision},
         "e2e": {"value": total_rollouts * args.steps / (ms_e2e * 1e-3), "unit": "rollouts/s",
-                "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e / args.steps},
+                "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roof,

@@ -1,0 +1,138 @@
+"""GPU parity of the tensor-core policy step (csrc/policy_tc.cu: tcgen05 GraphConv layers + fused decoder) against the
+golden traces recorded from the reference and against the fp32 CUDA path, under teacher forcing.
+
+What a 16-bit operand path can and cannot promise (rounding only the *weights* of the reference to
+bf16 already moves log-probabilities by up to 0.16 and flips 0.58 % of decisions on this kind of fixture):
+  * environment side (candidate sets, masks, costs, tour buffers): bit-exact, it is the same fp32 code;
+  * log-probabilities: absolute error bounded by LOGP_ATOL[precision] (measured maxima on these fixtures:
+    fp16 1.0e-2 at N=101, bf16 1.35e-1; tools/tc_parity_report.py prints them);
+  * greedy decisions: identical wherever the reference's top-2 log-prob gap exceeds DECISION_GAP[precision]."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.replay import env_args, load_case, start_nodes_of
+
+pytestmark = pytest.mark.gpu
+
+LOGP_ATOL = {"fp16": 2.5e-2, "bf16": 2.5e-1}
+DECISION_GAP = {"fp16": 3e-3, "bf16": 5e-2}
+EMB_ATOL = {"fp16": 4e-3, "bf16": 3e-2}      # h_fin / node_emb against the fp32 CUDA path (values are O(1))
+CASES = ["g21_pomo", "g101_pomo", "g51_sampling", "g51_upd2", "g31_k2"]
+
+
+def _make(g, precision):
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.weights import random_state_dict
+    env = RPEnv(inference=True, device="cuda", **env_args(g["env_kwargs"]))
+    env.seed(1)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision)
+    pol.load_state_dict(random_state_dict(int(g["policy_seed"])))
+    pol.eval()
+    pol.return_logp = True
+    env.load_data(g["instances"], dist_mat=torch.from_numpy(g["static_dist"]))
+    return env, pol
+
+
+def _sn(g):
+    sn = start_nodes_of(g)
+    return None if sn is None else sn.to(torch.int32)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_teacher_forced_tc(name, precision):
+    g = load_case(name)
+    env, pol = _make(g, precision)
+    envr, polr = _make(g, "fp32")
+    obs, obr = env.reset(start_nodes=_sn(g)), envr.reset(start_nodes=_sn(g))
+    T = g["trace_action"].shape[0]
+    worst, flips, n_dec = 0.0, 0, 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        for t in range(T):
+            assert np.array_equal(obs.nbh.cpu().numpy(), g["trace_nbh"][t]), f"nbh step {t}"
+            assert np.array_equal(obs.nbh_mask.cpu().numpy(), g["trace_mask"][t]), f"mask step {t}"
+            pol(obs)
+            polr(obr)
+            lp = pol.log_probs(env).cpu().numpy()
+            ref = g["trace_logp"][t]
+            fin = np.isfinite(ref)
+            assert np.array_equal(np.isfinite(lp), fin), f"support step {t}"
+            err = float(np.abs(lp - ref)[fin].max())
+            worst = max(worst, err)
+            assert err <= LOGP_ATOL[precision], (t, err)
+            if env._graph_fresh:
+                assert float((env.state["h_fin"] - envr.state["h_fin"]).abs().max()) <= EMB_ATOL[precision], t
+                assert float((env.state["ne"] - envr.state["ne"]).abs().max()) <= EMB_ATOL[precision], t
+            if g["decode"] == "greedy":
+                srt = np.sort(ref, -1)
+                decisive = (srt[:, -1] - srt[:, -2]) > DECISION_GAP[precision]
+                mine = env.state["action"].cpu().numpy()
+                same = (mine == g["trace_action"][t]).all(-1)
+                assert same[decisive].all(), f"decisive greedy action differs at step {t}"
+                flips += int((~same).sum())
+                n_dec += same.size
+            act = torch.from_numpy(g["trace_action"][t].astype(np.int64))
+            obs, cost, done, _ = env.step(act)
+            obr, _, _, _ = envr.step(act)
+            if not done:
+                assert np.array_equal(cost.cpu().numpy(), g["trace_cost"][t]), f"cost step {t}"
+    assert done
+    assert np.array_equal(env.tour_plan.cpu().numpy(), g["final_tour_plan"])
+    print(f"{name}/{precision}: worst |dlogp| {worst:.2e}, {flips}/{n_dec} near-tie decisions differ")
+
+
+@pytest.mark.parametrize("precision", ["fp16"])
+@pytest.mark.parametrize("name", ["g21_pomo", "g31_k2", "g51_upd2"])
+def test_fused_rollout_tc(name, precision):
+    """Free-running device loop on the tensor-core path: every rollout whose reference decisions are all decisive
+    reproduces the reference tours; the step API and the fused loop agree bit for bit with each other."""
+    from jampr_plus_b200.driver import rollout
+    g = load_case(name)
+    env, pol = _make(g, precision)
+    pol.return_logp = False
+    srt = np.sort(g["trace_logp"], -1)
+    decided = ((srt[..., -1] - srt[..., -2]) > DECISION_GAP[precision]).all(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        env.reset(start_nodes=_sn(g))
+        total, info = rollout(pol, env)
+        plan_fused = env.tour_plan.clone()
+        assert info["done_step"] >= 0
+        assert decided.any()
+        assert np.array_equal(plan_fused.cpu().numpy()[decided], g["final_tour_plan"][decided])
+        env.load_data(g["instances"], dist_mat=torch.from_numpy(g["static_dist"]))
+        obs = env.reset(start_nodes=_sn(g))
+        done = False
+        while not done:
+            action, _, _ = pol(obs)
+            obs, _, done, _ = env.step(action)
+    assert torch.equal(env.tour_plan, plan_fused)
+    assert torch.equal(env.total_cost, total)
+
+
+def test_tc_sampling_uses_given_uniforms():
+    """Sampling decode on the tensor-core path: the action is the inverse-CDF pick of the kernel's own
+    log-probabilities for the caller's uniforms (same rule as the fp32 path / oracle.select_inverse_cdf)."""
+    from oracle.policy_oracle import select_inverse_cdf
+    g = load_case("g51_sampling")
+    env, pol = _make(g, "fp16")
+    pol.set_decode_type("sampling")
+    obs = env.reset()
+    gen = torch.Generator().manual_seed(11)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        for t in range(20):
+            u = torch.rand(env.bs, generator=gen)
+            action, ll, ent = pol(obs, uniforms=u)
+            logp = pol.log_probs(env).cpu()
+            act_o, ll_o = select_inverse_cdf(logp, obs.nbh.cpu().long(), u)
+            assert torch.equal(action.cpu(), act_o), f"step {t}"
+            assert torch.equal(ll.cpu(), ll_o)
+            assert torch.isfinite(ent)
+            obs, _, done, _ = env.step(action)
+            if done:
+                break
