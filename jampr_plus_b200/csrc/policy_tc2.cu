@@ -1,0 +1,854 @@
+// Tensor-core policy step, two CTAs per SM (sm_100a).  Same math as policy_tc.cu (tour-graph GNN on tcgen05, node
+// embedding projection, per-tour embeddings, pointer decoder, selection: tour_encoder.py:159-243, policy.py:170-227,
+// attn_decoder.py:62-98), re-tiled so that TWO rollouts are resident per SM and hide each other's latencies:
+//   * 256 threads per CTA (8 warps: TMEM lane quarter = warp & 3, accumulator column half = warp >> 2), <= 128
+//     registers, 256 TMEM columns, <= 113 KB shared memory:
+//       - operand tiles cut to ceil(N/8) row groups (13 KB instead of 16 KB per tile at N = 101; the MMA still reads
+//         128 rows, the overhang lands in mapped shared memory and only feeds accumulator rows >= N, never read);
+//       - two 16 KB weight stages, each filled twice per layer (lin_root pair, then lin_rel pair);
+//       - the node embedding is parked in the operand type (16-bit) over the dead operand tiles;
+//       - decoder scratch overlays the weight stages and the edge tables.
+//   * layer epilogue in two passes over the thread's 64 accumulator columns (pass 1 parks GELU + skip back into the
+//     accumulator columns of TMEM and reduces the LayerNorm statistics, pass 2 normalises).
+// One CTA = one rollout = one step.  See policy_tc.cu for the single-CTA-per-SM variant with fp32 parked embeddings.
+#include "policy_tc_common.cuh"
+
+#define P2_THREADS 256
+#define P2_WARPS (P2_THREADS / 32)
+#define P2_GROUPS ((P2_THREADS - 32) / 16)   // customer rows aggregated concurrently (warps 1..7)
+#define NE16_STRIDE 528                       // bytes per parked node-embedding row: 256 x 16 bit + 16 (bank shift 4 words)
+#define QP2_STRIDE 260
+
+template <typename T>
+__device__ __forceinline__ void load_w2(uint8_t* sW, int slot, const void* w16, int img, uint64_t* full) {
+  mbar_arrive_expect_tx(&full[slot], 16384u);
+  bulk_g2s(sW + slot * 16384, reinterpret_cast<const uint8_t*>(w16) + ((size_t)(W16_ENC + img * W16_STAGE)) * 2, 16384u,
+           &full[slot]);
+}
+
+template <typename T>
+__device__ __forceinline__ void agg_nbh_tc2(uint8_t* sA, uint32_t ts, uint32_t tab_saddr, int k4, uint32_t dtab_saddr,
+                                            int nd, int N) {
+  using T2 = typename Elem<T>::T2;
+  const int tid = threadIdx.x;
+  const uint32_t h_saddr = smem_u32(sA) + 2u * ts;
+  if (tid < 32) {
+    const int cc = tid & 15, half = tid >> 4;
+    const uint32_t kboff = (uint32_t)(cc >> 3) * ts, c = cc & 7;
+    uint4 r = agg_run<T>(dtab_saddr, half * (nd >> 1), (half + 1) * (nd >> 1), h_saddr + kboff, c << 4);
+    r.x = as_u32(__hmax2(from_u32<T2>(r.x), from_u32<T2>(__shfl_xor_sync(0xffffffffu, r.x, 16))));
+    r.y = as_u32(__hmax2(from_u32<T2>(r.y), from_u32<T2>(__shfl_xor_sync(0xffffffffu, r.y, 16))));
+    r.z = as_u32(__hmax2(from_u32<T2>(r.z), from_u32<T2>(__shfl_xor_sync(0xffffffffu, r.z, 16))));
+    r.w = as_u32(__hmax2(from_u32<T2>(r.w), from_u32<T2>(__shfl_xor_sync(0xffffffffu, r.w, 16))));
+    if (half == 0) *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = r;
+  } else {
+    const int g = (tid - 32) >> 4, cc = (tid - 32) & 15;
+    const uint32_t kboff = (uint32_t)(cc >> 3) * ts, c = cc & 7;
+    for (int u = 1 + g; u < N; u += P2_GROUPS) {
+      const uint4 r = agg_run<T>(tab_saddr + (uint32_t)(u * k4) * 4u, 0, k4, h_saddr + kboff, c << 4);
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, c)) = r;
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void agg_tour_tc2(uint8_t* sA, uint32_t ts, const uint32_t* s_ltab, uint32_t etab_saddr,
+                                             int n_e4, int N) {
+  using T2 = typename Elem<T>::T2;
+  const int tid = threadIdx.x;
+  const uint32_t h_saddr = smem_u32(sA) + 2u * ts;
+  if (tid < 32) {
+    if (tid < 16) {
+      const uint32_t kboff = (uint32_t)(tid >> 3) * ts, c = tid & 7;
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      if (n_e4 > 0) r = agg_run<T>(etab_saddr, 0, n_e4, h_saddr + kboff, c << 4);
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = r;
+    }
+  } else {
+    const int g = (tid - 32) >> 4, cc = (tid - 32) & 15;
+    const uint32_t kboff = (uint32_t)(cc >> 3) * ts, c = cc & 7;
+    for (int u = 1 + g; u < N; u += P2_GROUPS) {
+      T2 m[4];
+      agg_edge<T>(s_ltab[u], h_saddr + kboff, c << 4, m, true);
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, c)) = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
+    }
+  }
+}
+
+// y = GELU(acc + b) + skip for 32 columns; accumulates the packed LayerNorm partials
+__device__ __forceinline__ void epi_pass1(uint32_t (&acc)[32], const uint32_t (&sk)[32], uint32_t pb, float2& s2, float2& q2) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b4 = lds_f32x4(pb + i * 16);
+    float2 y0 = gelu2(__fadd2_rn(make_float2(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1])), make_float2(b4.x, b4.y)));
+    float2 y1 = gelu2(__fadd2_rn(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), make_float2(b4.z, b4.w)));
+    y0 = __fadd2_rn(y0, make_float2(__uint_as_float(sk[4 * i]), __uint_as_float(sk[4 * i + 1])));
+    y1 = __fadd2_rn(y1, make_float2(__uint_as_float(sk[4 * i + 2]), __uint_as_float(sk[4 * i + 3])));
+    s2 = __fadd2_rn(s2, __fadd2_rn(y0, y1));
+    q2 = __ffma2_rn(y0, y0, q2);
+    q2 = __ffma2_rn(y1, y1, q2);
+    acc[4 * i] = __float_as_uint(y0.x); acc[4 * i + 1] = __float_as_uint(y0.y);
+    acc[4 * i + 2] = __float_as_uint(y1.x); acc[4 * i + 3] = __float_as_uint(y1.y);
+  }
+}
+
+// Layer epilogue, two passes.  Thread (q, lane, ch): row 32q + lane, accumulator columns 64ch .. 64ch+63.
+template <typename T>
+__device__ __forceinline__ void layer_epilogue2(uint32_t tmem, uint8_t* sA, uint32_t ts, float2* s_red, uint32_t par_saddr,
+                                                int N, float* __restrict__ hfin) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, ch = warp >> 2, r = q * 32 + lane;
+  const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16);
+  float2 s2 = make_float2(0.0f, 0.0f), q2 = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    const int col0 = ch * 64 + c * 32;
+    uint32_t acc[32], sk[32];
+    tmem_ld32_nowait(ta + col0, acc);
+    tmem_ld32_nowait(ta + 128 + col0, sk);
+    tmem_wait_ld();
+    epi_pass1(acc, sk, par_saddr + (uint32_t)col0 * 4u, s2, q2);
+    tmem_st32(ta + col0, acc);
+  }
+  tmem_wait_st();
+  s_red[ch * 128 + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
+  __syncthreads();
+  const float2 v0 = s_red[r], v1 = s_red[128 + r];
+  const float mean = (v0.x + v1.x) * (1.0f / 128.0f);
+  const float var = fmaxf(fmaf(-mean, mean, (v0.y + v1.y) * (1.0f / 128.0f)), 0.0f);
+  const float2 rstd2 = f2(rsqrtf(var + 1e-5f)), nmean2 = f2(-mean);
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    const int col0 = ch * 64 + c * 32;
+    const uint32_t pb = par_saddr + (uint32_t)col0 * 4u;
+    uint32_t acc[32];
+    tmem_ld32_nowait(ta + col0, acc);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 g4 = lds_f32x4(pb + 512 + i * 16), e4 = lds_f32x4(pb + 1024 + i * 16);
+      const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1])), nmean2);
+      const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), nmean2);
+      const float2 o0 = __ffma2_rn(d0, __fmul2_rn(make_float2(g4.x, g4.y), rstd2), make_float2(e4.x, e4.y));
+      const float2 o1 = __ffma2_rn(d1, __fmul2_rn(make_float2(g4.z, g4.w), rstd2), make_float2(e4.z, e4.w));
+      acc[4 * i] = __float_as_uint(o0.x); acc[4 * i + 1] = __float_as_uint(o0.y);
+      acc[4 * i + 2] = __float_as_uint(o1.x); acc[4 * i + 3] = __float_as_uint(o1.y);
+    }
+    tmem_st32(ta + 128 + col0, acc);
+    if (r < N) {
+      uint8_t* tile = sA + (2 + ch) * ts;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          pk[e] = as_u32(Elem<T>::from2(__uint_as_float(acc[i * 8 + 2 * e]), __uint_as_float(acc[i * 8 + 2 * e + 1])));
+        *reinterpret_cast<uint4*>(tile + sw128_off(r, c * 4 + i)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      if (hfin) {
+        float4* dst = reinterpret_cast<float4*>(hfin + (size_t)r * 128 + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                               __uint_as_float(acc[4 * i + 3]));
+      }
+    }
+  }
+  tmem_wait_st();
+}
+
+// decoder mat-vec partials, 256 threads: y[o] = sum_c x[c] W[c][o]; thread = OPT adjacent outputs x one K-slice;
+// partial sums at s_part[(slice * NV + v) * 256 + o]
+template <typename T, int OPT, int NV>
+__device__ __forceinline__ void matvec2(const T* __restrict__ W, int K, uint32_t x_saddr, int xstride, float* s_part) {
+  using T2 = typename Elem<T>::T2;
+  constexpr int NG = 256 / OPT, NS = P2_THREADS / NG;
+  const int og = threadIdx.x % NG, ks = threadIdx.x / NG;
+  const int kn = K / NS, k0 = ks * kn;
+  float acc[NV][OPT];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) acc[v][j] = 0.0f;
+  const T* wp = W + (size_t)k0 * 256 + og * OPT;
+  const uint32_t xa = x_saddr + (uint32_t)k0 * 4u;
+#pragma unroll 8
+  for (int c = 0; c < kn; ++c) {
+    float wv[OPT];
+    if constexpr (OPT == 8) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)c * 256));
+      const float2 f0 = Elem<T>::to2(from_u32<T2>(raw.x)), f1 = Elem<T>::to2(from_u32<T2>(raw.y));
+      const float2 f2_ = Elem<T>::to2(from_u32<T2>(raw.z)), f3 = Elem<T>::to2(from_u32<T2>(raw.w));
+      wv[0] = f0.x; wv[1] = f0.y; wv[2] = f1.x; wv[3] = f1.y; wv[4] = f2_.x; wv[5] = f2_.y; wv[6] = f3.x; wv[7] = f3.y;
+    } else {
+      static_assert(OPT == 2, "OPT must be 8 or 2");
+      const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(wp + (size_t)c * 256));
+      const float2 f0 = Elem<T>::to2(from_u32<T2>(raw));
+      wv[0] = f0.x; wv[1] = f0.y;
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float xv = lds_f32(xa + (uint32_t)(v * xstride + c) * 4u);
+#pragma unroll
+      for (int j = 0; j < OPT; j += 2) {
+        const float2 a2 = __ffma2_rn(make_float2(wv[j], wv[j + 1]), f2(xv), make_float2(acc[v][j], acc[v][j + 1]));
+        acc[v][j] = a2.x;
+        acc[v][j + 1] = a2.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < OPT; ++j) s_part[(ks * NV + v) * 256 + og * OPT + j] = acc[v][j];
+}
+
+__host__ __device__ inline uint32_t p2_al(uint32_t b) { return (b + 15u) & ~15u; }
+__host__ __device__ inline uint32_t p2_tile_stride(int N) { return (uint32_t)((N + 7) / 8) * 1024u; }
+// bytes of the region shared by the edge tables (GNN phase) and decoder scratch (decoder phase)
+__host__ __device__ inline uint32_t p2_r2_bytes(int N, int k, int A) {
+  const uint32_t k4 = (uint32_t)(k + 3) & ~3u, nd = (uint32_t)(N + 7) & ~7u;
+  const uint32_t tabs = p2_al((uint32_t)N * k4 * 4) + p2_al(nd * 4) + 2 * p2_al((uint32_t)N * 4) + 2 * p2_al((uint32_t)(N + 4) * 4);
+  const uint32_t dec = 2048 + 4096 + 2048 + 512 + 2048 + p2_al(16u * A) + p2_al(4u * A);
+  return tabs > dec ? tabs : dec;
+}
+// bytes of the region shared by the weight stages (GNN phase) and decoder scratch (decoder phase)
+#define P2_R1_BYTES 32768u
+
+template <typename T>
+__global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const PtArgs a) {
+  using T2 = typename Elem<T>::T2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const jampr_dims_t& d = a.d;
+  const jampr_state_t& st = a.st;
+  const jampr_instances_t& p = a.p;
+  const int done_step = st.ctl[JAMPR_CTL_DONE_STEP];
+  if (done_step >= 0 && done_step < a.step_no) return;
+  const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh, A = K * k, L = d.plan_len;
+  const int k4 = (k + 3) & ~3, nd = (N + 7) & ~7;
+  const int b = blockIdx.x, ins = b / d.n_samples;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* __restrict__ w = a.w;
+  const T* __restrict__ w16 = reinterpret_cast<const T*>(a.w16);
+  const bool fresh = a.graph_fresh != 0;
+  const uint32_t ts = p2_tile_stride(N);
+
+  // ---------------------------------------------------------------- shared memory carve-up
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = base;                       // 4 operand tiles of `ts` bytes: agg (K-blocks 0,1), h (K-blocks 2,3)
+  uint8_t* sW = base + 4 * ts;              // 2 weight stages (region R1)
+  uint8_t* s_ne16 = base;                   // parked node embedding rows (16-bit), over sA (+ the head of sW)
+  uint8_t* r1 = sW + 1024;                  // decoder scratch over the weight stages (first KB: tail of s_ne16)
+  uint32_t off = 4 * ts + P2_R1_BYTES;
+  uint8_t* r2 = base + off;                 // edge tables | decoder scratch
+  off += p2_r2_bytes(N, k, A);
+  auto take = [&](uint32_t bytes) {
+    uint8_t* rr = base + off;
+    off += p2_al(bytes);
+    return rr;
+  };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(take(32));     // full[0..1], root, acc
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(take(16));
+  float2* s_red = reinterpret_cast<float2*>(take(2 * 128 * sizeof(float2)));
+  float* s_par = reinterpret_cast<float*>(take(384 * 4));              // current layer: bias | gamma | beta
+  int* s_cnt = reinterpret_cast<int*>(take(16));
+  int16_t* s_plan = reinterpret_cast<int16_t*>(take((uint32_t)K * L * 2));
+  float* s_qt = reinterpret_cast<float*>(take(4 * JAMPR_MAX_SLOTS * 4));
+  float* s_lt = reinterpret_cast<float*>(take(JAMPR_MAX_SLOTS * 4));
+  float* s_P = reinterpret_cast<float*>(take(4 * JAMPR_MAX_SLOTS * 4));
+  float* s_feat = reinterpret_cast<float*>(take((uint32_t)K * 8 * 4));
+  int* s_nbh = reinterpret_cast<int*>(take((uint32_t)A * 4));
+  int8_t* s_pos = reinterpret_cast<int8_t*>(take((uint32_t)K * N));    // slot t, node n -> candidate index j or -1
+  uint8_t* s_mask = take(A);
+  int* s_idx = reinterpret_cast<int*>(take(JAMPR_MAX_SLOTS * 4));
+  // region R2 during the GNN: edge tables
+  uint32_t o2 = 0;
+  auto take2 = [&](uint32_t bytes) {
+    uint8_t* rr = r2 + o2;
+    o2 += p2_al(bytes);
+    return rr;
+  };
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(take2((uint32_t)N * k4 * 4));
+  uint32_t* s_dtab = reinterpret_cast<uint32_t*>(take2((uint32_t)nd * 4));
+  uint32_t* s_lf = reinterpret_cast<uint32_t*>(take2((uint32_t)N * 4));
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(take2((uint32_t)N * 4));
+  uint32_t* s_ef = reinterpret_cast<uint32_t*>(take2((uint32_t)(N + 4) * 4));
+  uint32_t* s_er = reinterpret_cast<uint32_t*>(take2((uint32_t)(N + 4) * 4));
+  // region R2 during the decoder (tables are dead after the last aggregation)
+  float* s_mean = reinterpret_cast<float*>(r2);                        // [4][128]
+  float* s_stat = reinterpret_cast<float*>(r2 + 2048);                 // [4][256]: sum half0/1, max half0/1
+  float4* s_sn4 = reinterpret_cast<float4*>(r2 + 6144);                // per node: glimpse score of the 4 heads
+  float* s_ln = reinterpret_cast<float*>(r2 + 8192);                   // per node: logit dot product
+  float4* s_pn4 = reinterpret_cast<float4*>(r2 + 8704);                // per node: glimpse weight of the 4 heads
+  float* s_sc = reinterpret_cast<float*>(r2 + 10752);                  // [4][A]
+  float* s_logit = reinterpret_cast<float*>(r2 + 10752 + p2_al(16u * A));
+  // region R1 during the decoder (weight stages are dead after the projection MMAs)
+  float* s_part = reinterpret_cast<float*>(r1);                        // 8 KB
+  float* s_te = reinterpret_cast<float*>(r1 + 8192);                   // [4][256]
+  float* s_q = reinterpret_cast<float*>(r1 + 12288);                   // [512]
+  float* s_ctxt = reinterpret_cast<float*>(r1 + 14336);                // [256]
+  float* s_qp = reinterpret_cast<float*>(r1 + 15360);                  // [4][260]
+  float* s_gbar = reinterpret_cast<float*>(r1 + 19520);                // [4][260]
+  float* s_g = reinterpret_cast<float*>(r1 + 23680);                   // [256]
+  float* s_lp = reinterpret_cast<float*>(r1 + 24704);                  // [256]  (ends at 25728 <= 31744)
+  uint64_t* full = bars;
+  uint64_t* bar_root = bars + 2;
+  uint64_t* bar_acc = bars + 3;
+
+  // ---------------------------------------------------------------- prologue
+  if (fresh) {
+    if (tid == 0) {
+      mbar_init(&full[0], 1);
+      mbar_init(&full[1], 1);
+      mbar_init(bar_root, 1);
+      mbar_init(bar_acc, 1);
+      mbar_fence_init();
+      load_w2<T>(sW, 0, a.w16, 2, full);       // layer 0, lin_root pair (K-blocks 2,3)
+      load_w2<T>(sW, 1, a.w16, 3, full);
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    for (uint32_t e = tid; e < (4 * ts) / 16; e += P2_THREADS) reinterpret_cast<uint4*>(sA)[e] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (tid < 4) s_cnt[tid] = 0;
+  for (int e = tid; e < K * N; e += P2_THREADS) s_pos[e] = (int8_t)-1;
+  if (tid < K) {
+    const size_t bk = (size_t)b * K + tid;
+    const int row = st.row[bk];
+    s_feat[tid * 8 + 0] = (float)st.cur[bk];
+    s_feat[tid * 8 + 1] = st.cap[bk];
+    s_feat[tid * 8 + 2] = st.time[bk];
+    s_feat[tid * 8 + 3] = st.cttd[bk];
+    s_feat[tid * 8 + 4] = (float)(d.k_max - row) / (float)d.k_max;
+  }
+  for (int e = tid; e < K * L; e += P2_THREADS) {
+    const int t = e / L, q = e - t * L;
+    s_plan[e] = st.plan[((size_t)b * d.k_max + st.row[(size_t)b * K + t]) * L + q];
+  }
+  for (int e = tid; e < A; e += P2_THREADS) {
+    s_nbh[e] = st.nbh[(size_t)b * A + e];
+    s_mask[e] = st.mask[(size_t)b * A + e];
+  }
+  __syncthreads();
+  for (int e = tid; e < A; e += P2_THREADS) s_pos[(e / k) * N + s_nbh[e]] = (int8_t)(e % k);
+  if (fresh) {
+    const int16_t* gk = p.knn + (size_t)ins * N * k;
+    const float* gw = p.knn_w + (size_t)ins * N * k;
+    for (int e = tid; e < N * k4; e += P2_THREADS) {
+      const int u = e / k4, j = min(e - u * k4, k - 1);
+      s_tab[e] = agg_entry((uint32_t)(uint16_t)gk[u * k + j], bits_T<T>(gw[u * k + j]));
+    }
+    const float* dist = p.dist + (size_t)ins * N * N;
+    for (int u = tid; u < nd; u += P2_THREADS) {
+      const int uu = min(u, N - 1);
+      s_dtab[u] = agg_entry((uint32_t)uu, bits_T<T>(p.ttd[(size_t)ins * N + uu]));
+    }
+    for (int u = tid; u < N; u += P2_THREADS) {
+      const int pr = st.pred[(size_t)b * N + u], su = st.succ[(size_t)b * N + u];
+      const bool vs = u > 0 && st.visited[(size_t)b * N + u] != 0;
+      s_lf[u] = vs ? agg_entry((uint32_t)pr, bits_T<T>(dist[(size_t)u * N + pr])) : 0u;
+      s_lr[u] = vs ? agg_entry((uint32_t)su, bits_T<T>(dist[(size_t)u * N + su])) : 0u;
+      if (vs) {
+        const uint32_t en = agg_entry((uint32_t)u, bits_T<T>(p.ttd[(size_t)ins * N + u]));
+        if (su == 0) s_ef[atomicAdd(&s_cnt[0], 1)] = en;
+        if (pr == 0) s_er[atomicAdd(&s_cnt[1], 1)] = en;
+      }
+    }
+  }
+  if (tid < K) {
+    int idx = 0;
+    while (idx < L && s_plan[tid * L + idx] != 0) ++idx;
+    s_idx[tid] = (idx >= L) ? 0 : idx;        // argmin over an all-nonzero row is position 0 (tour_encoder.py:236)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const int q4 = warp & 3, ch = warp >> 2, r = q4 * 32 + lane;      // epilogue role: row r, columns 64ch..64ch+63
+
+  if (fresh) {
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t idesc = umma_idesc(128, 128, Elem<T>::fmt);
+    const uint32_t a_addr = smem_u32(sA), w_addr = smem_u32(sW);
+    const int n_endf = s_cnt[0], n_endr = s_cnt[1];
+    const int n_ef4 = (n_endf + 3) & ~3, n_er4 = (n_endr + 3) & ~3;
+    if (tid < 3 && n_endf > 0 && n_endf + tid < n_ef4) s_ef[n_endf + tid] = s_ef[n_endf - 1];
+    if (tid >= 32 && tid < 35 && n_endr > 0 && n_endr + (tid - 32) < n_er4) s_er[n_endr + tid - 32] = s_er[n_endr - 1];
+    // ---- h_0 (hoisted node_emb_input_proj, per instance): fp32 -> TMEM skip columns, 16-bit -> h tiles
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = ch * 64 + c * 32;
+      uint32_t hv[32];
+      if (r < N) {
+        const float4* src = reinterpret_cast<const float4*>(p.h0 + ((size_t)ins * N + r) * 128 + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = __ldg(src + i);
+          hv[4 * i] = __float_as_uint(v.x); hv[4 * i + 1] = __float_as_uint(v.y);
+          hv[4 * i + 2] = __float_as_uint(v.z); hv[4 * i + 3] = __float_as_uint(v.w);
+        }
+        uint8_t* tile = sA + (2 + ch) * ts;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            pk[e] = as_u32(Elem<T>::from2(__uint_as_float(hv[i * 8 + 2 * e]), __uint_as_float(hv[i * 8 + 2 * e + 1])));
+          *reinterpret_cast<uint4*>(tile + sw128_off(r, c * 4 + i)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) hv[i] = 0u;
+      }
+      tmem_st32(ta + 128 + col0, hv);
+    }
+    tmem_wait_st();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t tab_saddr = smem_u32(s_tab), dtab_saddr = smem_u32(s_dtab), par_saddr = smem_u32(s_par);
+    const uint32_t ef_saddr = smem_u32(s_ef), er_saddr = smem_u32(s_er);
+    // layers 0..5 = GraphConv blocks; "layer" 6 = node_emb_output_proj (two 128-column halves, no aggregation)
+#pragma unroll 1
+    for (int l = 0; l < 7; ++l) {
+      const uint32_t ph = (uint32_t)(l & 1);
+      const bool proj = (l == 6);
+      if (tid == 0) {
+        // first weight pair: lin_root(h) (K-blocks 2,3) — or W_o rows 0..127 — overlaps the aggregation below
+        mbar_wait(&full[0], 0u);
+        mbar_wait(&full[1], 0u);
+        tc_fence_after();
+        mma_kblock(tmem, a_addr + 2 * ts, w_addr, idesc, true);
+        mma_kblock(tmem, a_addr + 3 * ts, w_addr + 16384, idesc, false);
+        umma_commit(bar_root);
+        mbar_wait(bar_root, ph);                     // both stages free again: stream the second pair
+        load_w2<T>(sW, 0, a.w16, l * 4 + (proj ? 2 : 0), full);
+        load_w2<T>(sW, 1, a.w16, l * 4 + (proj ? 3 : 1), full);
+      }
+      if (!proj) {
+        if (tid >= 32 && tid < 128)
+          reinterpret_cast<float4*>(s_par)[tid - 32] =
+              __ldg(reinterpret_cast<const float4*>(w + OFF_TE_BLK + (size_t)l * BLK_FLOATS + BLK_B) + (tid - 32));
+        if (l == 2 || l == 5) agg_nbh_tc2<T>(sA, ts, tab_saddr, k4, dtab_saddr, nd, N);
+        else if (l < 2) agg_tour_tc2<T>(sA, ts, s_lf, ef_saddr, n_ef4, N);
+        else agg_tour_tc2<T>(sA, ts, s_lr, er_saddr, n_er4, N);
+        fence_proxy_async();
+      }
+      __syncthreads();
+      if (proj) {
+        // per-tour mean of h over buffer positions 0..idx (one depot entry included, tour_encoder.py:236-243);
+        // overlaps the projection MMAs.  The edge tables are dead: s_mean overlays them (hence the barrier above).
+        for (int e = tid; e < K * 64; e += P2_THREADS) {
+          const int t = e >> 6, c2 = e & 63;
+          const uint32_t toff = (uint32_t)(2 + (c2 >> 5)) * ts;
+          const uint32_t chk = (uint32_t)(c2 & 31) >> 2, within = (uint32_t)(c2 & 3) * 4u;
+          const int idx = s_idx[t];
+          float sx = 0.0f, sy = 0.0f;
+          for (int q = 0; q <= idx; ++q) {
+            const uint32_t u = (uint32_t)s_plan[t * L + q];
+            const float2 v = Elem<T>::to2(*reinterpret_cast<const T2*>(sA + toff + sw128_off(u, chk) + within));
+            sx += v.x;
+            sy += v.y;
+          }
+          const float inv = 1.0f / (float)(idx + 1);
+          s_mean[t * 128 + 2 * c2] = sx * inv;
+          s_mean[t * 128 + 2 * c2 + 1] = sy * inv;
+        }
+      }
+      if (tid == 0) {
+        mbar_wait(&full[0], 1u);
+        mbar_wait(&full[1], 1u);
+        tc_fence_after();
+        if (!proj) {
+          mma_kblock(tmem, a_addr, w_addr, idesc, false);                   // lin_rel(agg): K-blocks 0,1
+          mma_kblock(tmem, a_addr + ts, w_addr + 16384, idesc, false);
+        } else {
+          mma_kblock(tmem + 128, a_addr + 2 * ts, w_addr, idesc, true);    // W_o rows 128..255
+          mma_kblock(tmem + 128, a_addr + 3 * ts, w_addr + 16384, idesc, false);
+        }
+        umma_commit(bar_acc);
+      }
+      if (proj) break;
+      mbar_wait(bar_acc, ph);
+      tc_fence_after();
+      if (tid == 0) {
+        const int nl = l + 1;                         // next layer's first pair
+        load_w2<T>(sW, 0, a.w16, nl * 4 + (nl == 6 ? 0 : 2), full);
+        load_w2<T>(sW, 1, a.w16, nl * 4 + (nl == 6 ? 1 : 3), full);
+      }
+      layer_epilogue2<T>(tmem, sA, ts, s_red, par_saddr, N,
+                         (l == 5 && a.store_cache) ? st.h_fin + (size_t)b * N * 128 : nullptr);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+    __syncthreads();          // per-tour means done: the h tiles may be overwritten by the parked embedding
+    // ---- node embedding rows: ne = acc + b + static_emb -> parked 16-bit rows (+ fp32 to HBM when cached)
+    mbar_wait(bar_acc, 0u);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int col0 = ch * 128 + c * 32;
+      uint32_t acc[32];
+      tmem_ld32_nowait(ta + col0, acc);
+      tmem_wait_ld();
+      if (r < N) {
+        const float4* se = reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + r) * 256 + col0);
+        const float4* bo = reinterpret_cast<const float4*>(w + OFF_TE_OUT_B + col0);
+        float4* gdst = a.store_cache ? reinterpret_cast<float4*>(st.ne + ((size_t)b * N + r) * 256 + col0) : nullptr;
+        uint8_t* dst = s_ne16 + (size_t)r * NE16_STRIDE + col0 * 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 sa = __ldg(se + 2 * i), sb = __ldg(se + 2 * i + 1), ba = __ldg(bo + 2 * i), bb = __ldg(bo + 2 * i + 1);
+          const float4 va = make_float4(__uint_as_float(acc[8 * i]) + ba.x + sa.x, __uint_as_float(acc[8 * i + 1]) + ba.y + sa.y,
+                                        __uint_as_float(acc[8 * i + 2]) + ba.z + sa.z, __uint_as_float(acc[8 * i + 3]) + ba.w + sa.w);
+          const float4 vb = make_float4(__uint_as_float(acc[8 * i + 4]) + bb.x + sb.x, __uint_as_float(acc[8 * i + 5]) + bb.y + sb.y,
+                                        __uint_as_float(acc[8 * i + 6]) + bb.z + sb.z, __uint_as_float(acc[8 * i + 7]) + bb.w + sb.w);
+          *reinterpret_cast<uint4*>(dst + i * 16) =
+              make_uint4(as_u32(Elem<T>::from2(va.x, va.y)), as_u32(Elem<T>::from2(va.z, va.w)),
+                         as_u32(Elem<T>::from2(vb.x, vb.y)), as_u32(Elem<T>::from2(vb.z, vb.w)));
+          if (gdst) { gdst[2 * i] = va; gdst[2 * i + 1] = vb; }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // cached tour-graph embedding (tour_encoder.py:163-166): per-tour means from h_fin, node embedding from ne
+    for (int e = tid; e < K * 128; e += P2_THREADS) {
+      const int t = e >> 7, c = e & 127;
+      const int idx = s_idx[t];
+      float sx = 0.0f;
+      for (int q = 0; q <= idx; ++q)
+        sx += from_T<T>(to_T<T>(st.h_fin[((size_t)b * N + s_plan[t * L + q]) * 128 + c]));
+      s_mean[t * 128 + c] = sx / (float)(idx + 1);
+    }
+    for (int e = tid; e < N * 32; e += P2_THREADS) {
+      const int u = e >> 5, c8 = (e & 31) * 8;
+      const float4* src = reinterpret_cast<const float4*>(st.ne + ((size_t)b * N + u) * 256 + c8);
+      const float4 va = src[0], vb = src[1];
+      *reinterpret_cast<uint4*>(s_ne16 + (size_t)u * NE16_STRIDE + c8 * 2) =
+          make_uint4(as_u32(Elem<T>::from2(va.x, va.y)), as_u32(Elem<T>::from2(va.z, va.w)),
+                     as_u32(Elem<T>::from2(vb.x, vb.y)), as_u32(Elem<T>::from2(vb.z, vb.w)));
+    }
+  }
+  __syncthreads();
+  if (fresh && warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(*tmem_slot, 256);
+  }
+
+  // ---------------------------------------------------------------- decoder
+  const uint32_t ne_saddr = smem_u32(s_ne16), te_saddr = smem_u32(s_te);
+  // (b) tour_emb[t] = folded tour-feature branch + W_to2 mean_h[t]          (tour_encoder.py:202-213)
+  matvec2<T, 2, 4>(w16 + W16_TO2, 128, smem_u32(s_mean), 128, s_part);     // NV = 4 >= K slots (K <= 4 here)
+  // (a) column mean / max of node_emb over the nodes (policy.py:179-181): thread = column pair x row parity
+  {
+    const int c2 = tid & 127, half = tid >> 7;
+    float2 sm = make_float2(0.0f, 0.0f), mx = make_float2(-INFINITY, -INFINITY);
+    for (int n = half; n < N; n += 2) {
+      const float2 v = Elem<T>::to2(*reinterpret_cast<const T2*>(s_ne16 + (size_t)n * NE16_STRIDE + c2 * 4));
+      sm.x += v.x; sm.y += v.y;
+      mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y);
+    }
+    *reinterpret_cast<float2*>(s_stat + half * 256 + 2 * c2) = sm;
+    *reinterpret_cast<float2*>(s_stat + (2 + half) * 256 + 2 * c2) = mx;
+  }
+  __syncthreads();
+  {
+    const float nmean = (s_stat[tid] + s_stat[256 + tid]) / (float)N;
+    const float nmax = fmaxf(s_stat[512 + tid], s_stat[768 + tid]);
+    if (a.store_cache && fresh) {
+      st.ne_stats[(size_t)b * 512 + tid] = nmean;
+      st.ne_stats[(size_t)b * 512 + 256 + tid] = nmax;
+    }
+    float sm = 0.0f, mx = -INFINITY;
+    for (int t = 0; t < K; ++t) {
+      float v = __ldg(w + OFF_TOF_B + tid);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) v = fmaf(s_feat[t * 8 + i], __ldg(w + OFF_TOF_WT + i * 256 + tid), v);
+      v += s_part[t * 256 + tid] + s_part[(4 + t) * 256 + tid];
+      s_te[t * 256 + tid] = v;
+      sm += v;
+      mx = fmaxf(mx, v);
+    }
+    s_q[tid] = nmean + sm / (float)K;
+    s_q[256 + tid] = nmax + mx;
+  }
+  __syncthreads();
+  // (c) ctxt = ctxt_proj(query)
+  matvec2<T, 8, 1>(w16 + W16_CTXT, 512, smem_u32(s_q), 0, s_part);
+  __syncthreads();
+  {
+    float v = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) v += s_part[ks * 256 + tid];
+    s_ctxt[tid] = v;
+  }
+  __syncthreads();
+  // (d) qp[h] = W_gk,h^T ctxt_h : K-slice ks (32 rows of set_proj) belongs to head ks / 2
+  matvec2<T, 8, 1>(w16 + W16_GK, 256, smem_u32(s_ctxt), 0, s_part);
+  __syncthreads();
+  for (int e = tid; e < 1024; e += P2_THREADS) {
+    const int h = e >> 8, c = e & 255;
+    s_qp[h * QP2_STRIDE + c] = s_part[(2 * h) * 256 + c] + s_part[(2 * h + 1) * 256 + c];
+  }
+  __syncthreads();
+  // (e) per-node and per-tour glimpse scores qp_h . node_emb[n], qp_h . tour_emb[t]: one warp per row; lane owns the
+  // column pairs 2 (lane + 32 i), i < 4, of the four query vectors in registers
+  {
+    float2 qv[4][4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[h][i] = *reinterpret_cast<const float2*>(s_qp + h * QP2_STRIDE + 2 * (lane + 32 * i));
+    for (int n = warp; n < N + K; n += P2_WARPS) {
+      float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 v;
+        if (n < N) v = Elem<T>::to2(*reinterpret_cast<const T2*>(s_ne16 + (size_t)n * NE16_STRIDE + (lane + 32 * i) * 4));
+        else v = *reinterpret_cast<const float2*>(s_te + (n - N) * 256 + 2 * (lane + 32 * i));
+        d0 = fmaf(v.x, qv[0][i].x, fmaf(v.y, qv[0][i].y, d0));
+        d1 = fmaf(v.x, qv[1][i].x, fmaf(v.y, qv[1][i].y, d1));
+        d2 = fmaf(v.x, qv[2][i].x, fmaf(v.y, qv[2][i].y, d2));
+        d3 = fmaf(v.x, qv[3][i].x, fmaf(v.y, qv[3][i].y, d3));
+      }
+      const float z = warp_sum4(d0, d1, d2, d3, lane);
+      if ((lane & 7) == 0) {
+        const int h = ((lane >> 4) << 1) | ((lane >> 3) & 1);
+        if (n < N) reinterpret_cast<float*>(s_sn4)[n * 4 + h] = z;
+        else s_qt[h * 8 + (n - N)] = z;
+      }
+    }
+  }
+  __syncthreads();
+  // (f) glimpse scores per action, softmax per head
+  for (int e = tid; e < 4 * A; e += P2_THREADS) {
+    const int h = e / A, aa = e - h * A;
+    const float sc = (reinterpret_cast<const float*>(s_sn4)[s_nbh[aa] * 4 + h] + s_qt[h * 8 + aa / k]) * 0.125f;
+    s_sc[e] = s_mask[aa] ? -INFINITY : sc;
+  }
+  __syncthreads();
+  if (warp < JAMPR_HEADS) {
+    float* sc = s_sc + warp * A;
+    float mx = -INFINITY;
+    for (int e = lane; e < A; e += 32) mx = fmaxf(mx, sc[e]);
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int e = lane; e < A; e += 32) {
+      const float ex = expf(sc[e] - mx);
+      sc[e] = ex;
+      sum += ex;
+    }
+    sum = warp_sum(sum);
+    for (int e = lane; e < A; e += 32) sc[e] = sc[e] / sum;
+  }
+  __syncthreads();
+  // glimpse weights folded onto nodes and tours (fixed summation order over the slots: deterministic)
+  for (int e = tid; e < 4 * N; e += P2_THREADS) {
+    const int n = e >> 2, h = e & 3;
+    float acc = 0.0f;
+    for (int t = 0; t < K; ++t) {
+      const int j = s_pos[t * N + n];
+      if (j >= 0) acc += s_sc[h * A + t * k + j];
+    }
+    reinterpret_cast<float*>(s_pn4)[e] = acc;
+  }
+  if (tid >= P2_THREADS - 32 && tid < P2_THREADS - 32 + 4 * K) {
+    const int e = tid - (P2_THREADS - 32), h = e / K, t = e - h * K;
+    float acc = 0.0f;
+    for (int j = 0; j < k; ++j) acc += s_sc[h * A + t * k + j];
+    s_P[h * 8 + t] = acc;
+  }
+  __syncthreads();
+  // (g) gbar[h] = sum_a p[h][a] act[a] = sum_t P[h][t] tour_emb[t] + sum_n pn[h][n] node_emb[n]
+  {
+    const int c2 = tid & 127, half = tid >> 7;
+    const uint32_t pn_saddr = smem_u32(s_pn4);
+    float2 g0 = make_float2(0.0f, 0.0f), g1 = g0, g2 = g0, g3 = g0;
+    for (int n = half; n < N; n += 2) {
+      const float2 v = Elem<T>::to2(*reinterpret_cast<const T2*>(s_ne16 + (size_t)n * NE16_STRIDE + c2 * 4));
+      const float4 pw = lds_f32x4(pn_saddr + (uint32_t)n * 16u);
+      g0 = __ffma2_rn(f2(pw.x), v, g0);
+      g1 = __ffma2_rn(f2(pw.y), v, g1);
+      g2 = __ffma2_rn(f2(pw.z), v, g2);
+      g3 = __ffma2_rn(f2(pw.w), v, g3);
+    }
+    if (half == 0) {
+      for (int t = 0; t < K; ++t) {
+        const float2 v = *reinterpret_cast<const float2*>(s_te + t * 256 + 2 * c2);
+        g0 = __ffma2_rn(f2(s_P[t]), v, g0);
+        g1 = __ffma2_rn(f2(s_P[8 + t]), v, g1);
+        g2 = __ffma2_rn(f2(s_P[16 + t]), v, g2);
+        g3 = __ffma2_rn(f2(s_P[24 + t]), v, g3);
+      }
+    }
+    *reinterpret_cast<float2*>(s_part + (half * 4 + 0) * 256 + 2 * c2) = g0;
+    *reinterpret_cast<float2*>(s_part + (half * 4 + 1) * 256 + 2 * c2) = g1;
+    *reinterpret_cast<float2*>(s_part + (half * 4 + 2) * 256 + 2 * c2) = g2;
+    *reinterpret_cast<float2*>(s_part + (half * 4 + 3) * 256 + 2 * c2) = g3;
+  }
+  __syncthreads();
+  for (int e = tid; e < 1024; e += P2_THREADS) {
+    const int h = e >> 8, c = e & 255;
+    s_gbar[h * QP2_STRIDE + c] = s_part[h * 256 + c] + s_part[(4 + h) * 256 + c];
+  }
+  __syncthreads();
+  // (h) glimpse g[o] = W_gv[o] . gbar[head(o)]
+  matvec2<T, 8, 1>(w16 + W16_GV, 256, smem_u32(s_gbar) + (uint32_t)((tid & 31) >> 3) * QP2_STRIDE * 4u, 0, s_part);
+  __syncthreads();
+  {
+    float v = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) v += s_part[ks * 256 + tid];
+    s_g[tid] = v;
+  }
+  __syncthreads();
+  // (i) lp = W_lk^T out_proj(g) = M1 g
+  matvec2<T, 8, 1>(w16 + W16_M1, 256, smem_u32(s_g), 0, s_part);
+  __syncthreads();
+  {
+    float v = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) v += s_part[ks * 256 + tid];
+    s_lp[tid] = v;
+  }
+  __syncthreads();
+  // (j) pointer logits: 10 tanh((lp . node_emb[n] + lp . tour_emb[t]) / 16)
+  {
+    float2 lv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lv[i] = *reinterpret_cast<const float2*>(s_lp + 2 * (lane + 32 * i));
+    for (int n = warp; n < N + K; n += P2_WARPS) {
+      float dd = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 v;
+        if (n < N) v = Elem<T>::to2(*reinterpret_cast<const T2*>(s_ne16 + (size_t)n * NE16_STRIDE + (lane + 32 * i) * 4));
+        else v = *reinterpret_cast<const float2*>(s_te + (n - N) * 256 + 2 * (lane + 32 * i));
+        dd = fmaf(v.x, lv[i].x, fmaf(v.y, lv[i].y, dd));
+      }
+      dd = warp_sum(dd);
+      if (lane == 0) {
+        if (n < N) s_ln[n] = dd;
+        else s_lt[n - N] = dd;
+      }
+    }
+  }
+  __syncthreads();
+  for (int aa = tid; aa < A; aa += P2_THREADS)
+    s_logit[aa] = s_mask[aa] ? -INFINITY : 10.0f * tanhf((s_ln[s_nbh[aa]] + s_lt[aa / k]) * 0.0625f);
+  __syncthreads();
+  // ---- log-softmax + selection (warp 0), same rules as decoder.cu
+  if (warp == 0) {
+    float mx = -INFINITY;
+    bool nan = false;
+    for (int e = lane; e < A; e += 32) {
+      const float v = s_logit[e];
+      nan |= (v != v);
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int e = lane; e < A; e += 32) sum += expf(s_logit[e] - mx);
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    float ent = 0.0f, best = -INFINITY;
+    int besti = 0x7fffffff;
+    for (int e = lane; e < A; e += 32) {
+      const float lpv = s_logit[e] - lse;
+      nan |= (lpv != lpv);
+      s_logit[e] = lpv;
+      if (st.logp) st.logp[(size_t)b * A + e] = lpv;
+      if (lpv >= -10000.0f) ent -= lpv * expf(lpv);
+      if (lpv > best) { best = lpv; besti = e; }
+    }
+    nan = __any_sync(0xffffffffu, nan);
+    ent = warp_sum(ent);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    int choice = besti;
+    if (a.decode_type == JAMPR_DECODE_SAMPLING) {
+      const float u = a.uniforms ? a.uniforms[b] : jampr_uniform(a.seed, (uint32_t)b, (uint32_t)a.step_no);
+      float run = 0.0f;
+      int hit = -1, lastf = -1;
+      for (int bs0 = 0; bs0 < A; bs0 += 32) {
+        const int e = bs0 + lane;
+        const float pe = (e < A) ? expf(s_logit[e]) : 0.0f;
+        float inc = pe;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const float cum = run + inc;
+        const unsigned hm = __ballot_sync(0xffffffffu, e < A && pe > 0.0f && cum > u);
+        const unsigned fm = __ballot_sync(0xffffffffu, e < A && pe > 0.0f);
+        if (hit < 0 && hm) hit = bs0 + __ffs(hm) - 1;
+        if (fm) lastf = bs0 + 31 - __clz(fm);
+        run = __shfl_sync(0xffffffffu, cum, 31);
+      }
+      choice = (hit >= 0) ? hit : lastf;
+      if (choice < 0) choice = 0;
+    }
+    if (lane == 0) {
+      if (choice >= A) choice = 0;
+      st.action[2 * (size_t)b] = choice / k;
+      st.action[2 * (size_t)b + 1] = s_nbh[choice];
+      st.ll[b] = s_logit[choice];
+      st.entropy[b] = ent;
+      if (nan) atomicOr(st.status + b, JAMPR_ST_NAN_LOGITS);
+    }
+  }
+}
+
+static size_t p2_smem_bytes(const jampr_dims_t* d) {
+  const int N = d->n_nodes, k = d->k_nbh, K = d->n_slots, A = K * k, L = d->plan_len;
+  size_t s = 1024 + 4 * (size_t)p2_tile_stride(N) + P2_R1_BYTES + p2_r2_bytes(N, k, A);
+  s += p2_al(32) + p2_al(16) + p2_al(2 * 128 * 8) + p2_al(384 * 4) + p2_al(16) + p2_al(K * L * 2);
+  s += 2 * p2_al(4 * JAMPR_MAX_SLOTS * 4) + p2_al(JAMPR_MAX_SLOTS * 4) + p2_al(K * 8 * 4) + p2_al(A * 4) + p2_al(K * N) + p2_al(A) +
+       p2_al(JAMPR_MAX_SLOTS * 4);
+  return s;
+}
+
+template <typename T>
+static int launch_p2(const PtArgs& a, size_t smem, cudaStream_t s) {
+  CUDA_RET(cudaFuncSetAttribute(policy_step_tc2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  policy_step_tc2_kernel<T><<<a.d.n_inst * a.d.n_samples, P2_THREADS, smem, s>>>(a);
+  return launch_status();
+}
+
+// Returns JAMPR_E_TOOLARGE when the configuration does not fit this tiling (caller falls back to policy_tc.cu).
+int jampr_policy_step_tc2(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                          const jampr_state_t* st, int graph_fresh, int step_no, int decode_type, uint64_t seed,
+                          const float* uniforms, int store_cache, cudaStream_t s) {
+  if (d->n_nodes > 128 || d->n_slots > 4 || d->k_nbh > 127) return JAMPR_E_TOOLARGE;
+  if (!w->blob_bf16 || w->n_bf16 < (int64_t)W16_END) return JAMPR_E_BADARG;
+  const int N = d->n_nodes, A = d->n_slots * d->k_nbh;
+  // the parked embedding (N rows of 528 B) must fit below the decoder scratch that overlays the weight stages
+  if ((size_t)N * NE16_STRIDE > 4 * (size_t)p2_tile_stride(N) + 1024) return JAMPR_E_TOOLARGE;
+  if (10752 + p2_al(16u * A) + p2_al(4u * A) > p2_r2_bytes(N, d->k_nbh, A)) return JAMPR_E_TOOLARGE;
+  const size_t smem = p2_smem_bytes(d);
+  if (smem > 227 * 1024) return JAMPR_E_TOOLARGE;
+  PtArgs a;
+  a.d = *d;
+  a.p = *inst;
+  a.st = *st;
+  a.w = w->blob;
+  a.w16 = w->blob_bf16;
+  a.uniforms = uniforms;
+  a.seed = seed;
+  a.step_no = step_no;
+  a.decode_type = decode_type;
+  a.graph_fresh = graph_fresh;
+  a.store_cache = store_cache;
+  if (w->precision == JAMPR_PREC_F16) return launch_p2<__half>(a, smem, s);
+  return launch_p2<__nv_bfloat16>(a, smem, s);
+}

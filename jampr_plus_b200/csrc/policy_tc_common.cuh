@@ -1,0 +1,158 @@
+// Shared device helpers of the tensor-core policy-step kernels (policy_tc.cu, policy_tc2.cu).
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace tc;
+
+// 16-bit weight blob (elements), mirrors packing.pack_tc
+#define W16_STAGE 8192                                  // one 16 KB stage = [128 rows][64 K] elements
+#define W16_ENC 0                                       // 7 x 4 stages: layers 0..5, then node_emb_output_proj
+#define W16_TO2 (W16_ENC + 28 * W16_STAGE)              // [128][256]  tour output_proj, per-tour-mean half, transposed
+#define W16_CTXT (W16_TO2 + 128 * 256)                  // [512][256]  ctxt_proj^T
+#define W16_GK (W16_CTXT + 512 * 256)                   // [256][256]  set_proj rows 0..255 as stored
+#define W16_GV (W16_GK + 256 * 256)                     // [256][256]  set_proj rows 256..511, transposed
+#define W16_M1 (W16_GV + 256 * 256)                     // [256][256]  (W_lk^T W_out)^T
+#define W16_END (W16_M1 + 256 * 256)
+
+struct PtArgs {
+  jampr_dims_t d;
+  jampr_instances_t p;
+  jampr_state_t st;
+  const float* w;        // fp32 blob (biases, LayerNorm, folded tour-feature matrix)
+  const void* w16;       // 16-bit blob
+  const float* uniforms;
+  uint64_t seed;
+  int step_no;
+  int decode_type;
+  int graph_fresh;
+  int store_cache;       // write h_fin / ne / ne_stats to HBM (needed when later steps reuse them)
+};
+
+template <typename T>
+__device__ __forceinline__ T to_T(float v);
+template <>
+__device__ __forceinline__ __half to_T<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_T<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <typename T>
+__device__ __forceinline__ float from_T(T v);
+template <>
+__device__ __forceinline__ float from_T<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float from_T<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ uint16_t bits_T(float v) {
+  T t = to_T<T>(v);
+  return *reinterpret_cast<uint16_t*>(&t);
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+
+// GELU(erf) on two values with the packed fp32 pipe (FFMA2 / FMUL2): erf to 1.5e-7 absolute
+// (Abramowitz-Stegun 7.1.26), well inside the 16-bit operand noise of this path.
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  float2 ax = __fmul2_rn(x, f2(0.70710678118654752f));
+  ax.x = fabsf(ax.x);
+  ax.y = fabsf(ax.y);
+  const float2 dn = __ffma2_rn(ax, f2(0.3275911f), f2(1.0f));
+  const float2 t = make_float2(rcp_approx(dn.x), rcp_approx(dn.y));
+  float2 p = __ffma2_rn(t, f2(-1.061405429f), f2(1.453152027f));      // coefficients negated: p = -poly
+  p = __ffma2_rn(t, p, f2(-1.421413741f));
+  p = __ffma2_rn(t, p, f2(0.284496736f));
+  p = __ffma2_rn(t, p, f2(-0.254829592f));
+  p = __fmul2_rn(p, t);
+  float2 z = __fmul2_rn(ax, ax);
+  z = __fmul2_rn(z, f2(-1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(z.x), ex2_approx(z.y));
+  const float2 ea = __ffma2_rn(p, e, f2(1.0f));                        // erf(|x| / sqrt 2)
+  const float2 hx = __fmul2_rn(x, f2(0.5f));
+  const float2 sg = make_float2(copysignf(ea.x, x.x), copysignf(ea.y, x.y));
+  return __ffma2_rn(sg, hx, hx);
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// ---- one K-block (64 of K) of a 128 x 128 tile product: 4 tcgen05.mma of K = 16
+__device__ __forceinline__ void mma_kblock(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_f16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+}
+
+// ---- max aggregation into the agg tiles (K-blocks 0,1), packed 16-bit math.
+// An edge is one 32-bit table entry: low half = byte offset of the source row inside an h tile with the row's
+// swizzle phase folded in (row * 128 | (row & 7) << 4), high half = the edge weight in the operand type.  The
+// 16-byte chunk c of that row then sits at (entry & 0xffff) ^ (c << 4).  Rows are padded to a multiple of four
+// entries by repeating the last edge (max is idempotent), so the table is read with 128-bit loads.
+__device__ __forceinline__ uint32_t agg_entry(uint32_t row, uint16_t wbits) {
+  return (row << 7) | ((row & 7u) << 4) | ((uint32_t)wbits << 16);
+}
+
+template <typename T>
+__device__ __forceinline__ void agg_edge(uint32_t e, uint32_t hb, uint32_t c4, typename Elem<T>::T2 (&m)[4], bool first) {
+  using T2 = typename Elem<T>::T2;
+  const T2 w2 = from_u32<T2>(__byte_perm(e, e, 0x3232));
+  const uint4 v = lds128(hb + ((e & 0xffffu) ^ c4));
+  const T2 p0 = __hmul2(from_u32<T2>(v.x), w2), p1 = __hmul2(from_u32<T2>(v.y), w2);
+  const T2 p2 = __hmul2(from_u32<T2>(v.z), w2), p3 = __hmul2(from_u32<T2>(v.w), w2);
+  if (first) { m[0] = p0; m[1] = p1; m[2] = p2; m[3] = p3; }
+  else { m[0] = __hmax2(m[0], p0); m[1] = __hmax2(m[1], p1); m[2] = __hmax2(m[2], p2); m[3] = __hmax2(m[3], p3); }
+}
+
+// max over entries [e0, e1) (both multiples of 4, e1 > e0) of weight * h[source] for one 16-byte chunk
+template <typename T>
+__device__ __forceinline__ uint4 agg_run(uint32_t tab_saddr, int e0, int e1, uint32_t hb, uint32_t c4) {
+  using T2 = typename Elem<T>::T2;
+  T2 m[4];
+  for (int j = e0; j < e1; j += 4) {
+    const uint4 q = lds128(tab_saddr + (uint32_t)j * 4u);
+    agg_edge<T>(q.x, hb, c4, m, j == e0);
+    agg_edge<T>(q.y, hb, c4, m, false);
+    agg_edge<T>(q.z, hb, c4, m, false);
+    agg_edge<T>(q.w, hb, c4, m, false);
+  }
+  return make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
+}
+
+// sum over the warp of four values at once: lane 16*(h>>1) + 8*(h&1) ends up with the total of value h
+__device__ __forceinline__ float warp_sum4(float d0, float d1, float d2, float d3, int lane) {
+  const bool up4 = (lane & 16) != 0, up3 = (lane & 8) != 0;
+  float x0 = up4 ? d2 : d0, x1 = up4 ? d3 : d1;
+  const float y0 = up4 ? d0 : d2, y1 = up4 ? d1 : d3;
+  x0 += __shfl_xor_sync(0xffffffffu, y0, 16);
+  x1 += __shfl_xor_sync(0xffffffffu, y1, 16);
+  float z = up3 ? x1 : x0;
+  const float sn = up3 ? x0 : x1;
+  z += __shfl_xor_sync(0xffffffffu, sn, 8);
+  z += __shfl_xor_sync(0xffffffffu, z, 4);
+  z += __shfl_xor_sync(0xffffffffu, z, 2);
+  z += __shfl_xor_sync(0xffffffffu, z, 1);
+  return z;
+}
+

@@ -2,6 +2,7 @@
 // Nothing here synchronises: every call only enqueues kernels on the caller's stream, so a rollout can be
 // captured into a CUDA graph by the caller.  Termination is data dependent (env.py:281) and lives in the
 // device control block; kernels launched after the terminating step return immediately.
+#include <stdlib.h>
 #include "common.cuh"
 
 int jampr_node_encoder_f32(const jampr_dims_t*, const jampr_instances_t*, const float*, cudaStream_t);
@@ -11,7 +12,25 @@ int jampr_decoder_launch(const jampr_dims_t*, const jampr_instances_t*, const ja
                          uint64_t, const float*, cudaStream_t);
 int jampr_policy_step_tc(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, const jampr_state_t*,
                          int, int, int, uint64_t, const float*, int, cudaStream_t);
+int jampr_policy_step_tc2(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, const jampr_state_t*,
+                          int, int, int, uint64_t, const float*, int, cudaStream_t);
 int64_t jampr_w16_elems(void);
+
+// Tensor-core policy step: the two-CTAs-per-SM tiling (policy_tc2.cu) when the graph fits it, else the one-CTA
+// tiling (policy_tc.cu).  JAMPR_TC_VARIANT=1 forces the latter (A/B measurements).
+static int policy_step_tc_any(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                              const jampr_state_t* st, int fresh, int step_no, int decode_type, uint64_t seed,
+                              const float* uniforms, int store_cache, cudaStream_t s) {
+  static const int variant = [] {
+    const char* e = getenv("JAMPR_TC_VARIANT");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  if (variant == 2) {
+    const int rc = jampr_policy_step_tc2(d, inst, w, st, fresh, step_no, decode_type, seed, uniforms, store_cache, s);
+    if (rc != JAMPR_E_TOOLARGE) return rc;
+  }
+  return jampr_policy_step_tc(d, inst, w, st, fresh, step_no, decode_type, seed, uniforms, store_cache, s);
+}
 
 static int check_policy_args(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w) {
   if (!d || !inst || !w || !w->blob || w->n_floats < (int64_t)OFF_END) return JAMPR_E_BADARG;
@@ -56,7 +75,7 @@ extern "C" int jampr_tour_encoder(const jampr_dims_t* d, const jampr_instances_t
   // on the tensor-core path the encoder is fused with the decoder: the call runs the whole policy step (greedy)
   // and additionally stores h_fin / ne / ne_stats
   if (w->precision != JAMPR_PREC_F32)
-    return jampr_policy_step_tc(d, inst, w, st, 1, step_no, JAMPR_DECODE_GREEDY, 0, nullptr, 1, s);
+    return policy_step_tc_any(d, inst, w, st, 1, step_no, JAMPR_DECODE_GREEDY, 0, nullptr, 1, s);
   return jampr_tour_encoder_f32(d, inst, st, w->blob, step_no, s);
 }
 
@@ -69,8 +88,8 @@ extern "C" int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t*
   if (!st->h_fin || !st->ne || !st->ne_stats) return JAMPR_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (w->precision != JAMPR_PREC_F32)
-    return jampr_policy_step_tc(d, inst, w, st, graph_fresh, step_no, decode_type, seed, uniforms,
-                                (d->upd_step != 1) || st->logp != nullptr, s);
+    return policy_step_tc_any(d, inst, w, st, graph_fresh, step_no, decode_type, seed, uniforms,
+                              (d->upd_step != 1) || st->logp != nullptr, s);
   if (graph_fresh) {
     rc = jampr_tour_encoder_f32(d, inst, st, w->blob, step_no, s);
     if (rc) return rc;
