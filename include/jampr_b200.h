@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define JAMPR_ABI_VERSION 1
+#define JAMPR_ABI_VERSION 2
 
 /* argument errors */
 #define JAMPR_E_BADARG   (-1)
@@ -80,6 +80,10 @@ typedef struct {
   int32_t*     inst_status;/* out (I) JAMPR_ST_TW_COLLAPSE */
   float*       static_emb; /* out (I,N,256) node-encoder output (node_encoder.py:128-155) */
   float*       h0;         /* out (I,N,128) node_emb_input_proj(static_emb) (tour_encoder.py:170-172), hoisted */
+  uint32_t*    tc_tab;     /* out (I,N,k4) k4 = k rounded up to 4: packed edges of the kNN graph for the tensor-core step
+                              (source-row offset | 16-bit weight, csrc/policy_tc_common.cuh agg_entry), written by
+                              jampr_node_encoder for the precision in use; may be NULL on the fp32 path */
+  uint32_t*    tc_dtab;    /* out (I,nd) nd = N rounded up to 8: packed edges node -> depot, same encoding */
   const float* dist_given; /* in  (I,N,N) or NULL: caller-supplied normalised transit matrix copied into `dist`
                               instead of evaluating the DIMACS formula (e.g. a matrix computed by torch on the
                               host: MKL's vsSqrt is not correctly rounded, sqrtf on the device is) */

@@ -311,17 +311,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   __syncthreads();
   for (int e = tid; e < A; e += PT_THREADS) s_pos[(e / k) * N + s_nbh[e]] = (int8_t)(e % k);
   if (fresh) {
-    const int16_t* gk = p.knn + (size_t)ins * N * k;
-    const float* gw = p.knn_w + (size_t)ins * N * k;
-    for (int e = tid; e < N * k4; e += PT_THREADS) {
-      const int u = e / k4, j = min(e - u * k4, k - 1);
-      s_tab[e] = agg_entry((uint32_t)(uint16_t)gk[u * k + j], bits_T<T>(gw[u * k + j]));
+    {
+      const uint4* gt = reinterpret_cast<const uint4*>(p.tc_tab + (size_t)ins * N * k4);
+      for (int e = tid; e < (N * k4) / 4; e += PT_THREADS) reinterpret_cast<uint4*>(s_tab)[e] = __ldg(gt + e);
+      const uint4* gd = reinterpret_cast<const uint4*>(p.tc_dtab + (size_t)ins * nd);
+      for (int e = tid; e < nd / 4; e += PT_THREADS) reinterpret_cast<uint4*>(s_dtab)[e] = __ldg(gd + e);
     }
     const float* dist = p.dist + (size_t)ins * N * N;
-    for (int u = tid; u < nd; u += PT_THREADS) {
-      const int uu = min(u, N - 1);
-      s_dtab[u] = agg_entry((uint32_t)uu, bits_T<T>(p.ttd[(size_t)ins * N + uu]));
-    }
     for (int u = tid; u < N; u += PT_THREADS) {
       const int pr = st.pred[(size_t)b * N + u], su = st.succ[(size_t)b * N + u];
       const bool vs = u > 0 && st.visited[(size_t)b * N + u] != 0;

@@ -202,6 +202,30 @@ __device__ __forceinline__ void matvec2(const T* __restrict__ W, int K, uint32_t
     for (int j = 0; j < OPT; ++j) s_part[(ks * NV + v) * 256 + og * OPT + j] = acc[v][j];
 }
 
+// Per-instance packed edge tables (once per episode, from jampr_node_encoder): kNN rows padded to a multiple of
+// four entries by repeating the last edge, and the node -> depot edges padded to a multiple of eight.
+template <typename T>
+__global__ void tc_prepare_kernel(jampr_dims_t d, jampr_instances_t p) {
+  const int N = d.n_nodes, k = d.k_nbh, k4 = (k + 3) & ~3, nd = (N + 7) & ~7, ins = blockIdx.x;
+  const int16_t* gk = p.knn + (size_t)ins * N * k;
+  const float* gw = p.knn_w + (size_t)ins * N * k;
+  for (int e = threadIdx.x; e < N * k4; e += blockDim.x) {
+    const int u = e / k4, j = min(e - u * k4, k - 1);
+    p.tc_tab[(size_t)ins * N * k4 + e] = agg_entry((uint32_t)(uint16_t)gk[u * k + j], bits_T<T>(gw[u * k + j]));
+  }
+  for (int u = threadIdx.x; u < nd; u += blockDim.x) {
+    const int uu = min(u, N - 1);
+    p.tc_dtab[(size_t)ins * nd + u] = agg_entry((uint32_t)uu, bits_T<T>(p.ttd[(size_t)ins * N + uu]));
+  }
+}
+
+int jampr_tc_prepare(const jampr_dims_t* d, const jampr_instances_t* inst, int precision, cudaStream_t s) {
+  if (!inst->tc_tab || !inst->tc_dtab) return JAMPR_E_BADARG;
+  if (precision == JAMPR_PREC_F16) tc_prepare_kernel<__half><<<d->n_inst, 256, 0, s>>>(*d, *inst);
+  else tc_prepare_kernel<__nv_bfloat16><<<d->n_inst, 256, 0, s>>>(*d, *inst);
+  return launch_status();
+}
+
 __host__ __device__ inline uint32_t p2_al(uint32_t b) { return (b + 15u) & ~15u; }
 __host__ __device__ inline uint32_t p2_tile_stride(int N) { return (uint32_t)((N + 7) / 8) * 1024u; }
 // bytes of the region shared by the edge tables (GNN phase) and decoder scratch (decoder phase)
@@ -331,17 +355,13 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   __syncthreads();
   for (int e = tid; e < A; e += P2_THREADS) s_pos[(e / k) * N + s_nbh[e]] = (int8_t)(e % k);
   if (fresh) {
-    const int16_t* gk = p.knn + (size_t)ins * N * k;
-    const float* gw = p.knn_w + (size_t)ins * N * k;
-    for (int e = tid; e < N * k4; e += P2_THREADS) {
-      const int u = e / k4, j = min(e - u * k4, k - 1);
-      s_tab[e] = agg_entry((uint32_t)(uint16_t)gk[u * k + j], bits_T<T>(gw[u * k + j]));
+    {
+      const uint4* gt = reinterpret_cast<const uint4*>(p.tc_tab + (size_t)ins * N * k4);
+      for (int e = tid; e < (N * k4) / 4; e += P2_THREADS) reinterpret_cast<uint4*>(s_tab)[e] = __ldg(gt + e);
+      const uint4* gd = reinterpret_cast<const uint4*>(p.tc_dtab + (size_t)ins * nd);
+      for (int e = tid; e < nd / 4; e += P2_THREADS) reinterpret_cast<uint4*>(s_dtab)[e] = __ldg(gd + e);
     }
     const float* dist = p.dist + (size_t)ins * N * N;
-    for (int u = tid; u < nd; u += P2_THREADS) {
-      const int uu = min(u, N - 1);
-      s_dtab[u] = agg_entry((uint32_t)uu, bits_T<T>(p.ttd[(size_t)ins * N + uu]));
-    }
     for (int u = tid; u < N; u += P2_THREADS) {
       const int pr = st.pred[(size_t)b * N + u], su = st.succ[(size_t)b * N + u];
       const bool vs = u > 0 && st.visited[(size_t)b * N + u] != 0;
@@ -471,13 +491,14 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         umma_commit(bar_acc);
       }
       if (proj) break;
-      mbar_wait(bar_acc, ph);
-      tc_fence_after();
       if (tid == 0) {
+        mbar_wait(bar_acc, ph);                       // one waiter; everybody else parks at the block barrier
         const int nl = l + 1;                         // next layer's first pair
         load_w2<T>(sW, 0, a.w16, nl * 4 + (nl == 6 ? 0 : 2), full);
         load_w2<T>(sW, 1, a.w16, nl * 4 + (nl == 6 ? 1 : 3), full);
       }
+      __syncthreads();
+      tc_fence_after();
       layer_epilogue2<T>(tmem, sA, ts, s_red, par_saddr, N,
                          (l == 5 && a.store_cache) ? st.h_fin + (size_t)b * N * 128 : nullptr);
       fence_proxy_async();
@@ -485,9 +506,9 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       __syncthreads();
       tc_fence_after();
     }
-    __syncthreads();          // per-tour means done: the h tiles may be overwritten by the parked embedding
     // ---- node embedding rows: ne = acc + b + static_emb -> parked 16-bit rows (+ fp32 to HBM when cached)
-    mbar_wait(bar_acc, 0u);
+    if (tid == 0) mbar_wait(bar_acc, 0u);
+    __syncthreads();          // projection complete and per-tour means done: the h tiles may be overwritten
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {

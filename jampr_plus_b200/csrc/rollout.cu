@@ -15,6 +15,7 @@ int jampr_policy_step_tc(const jampr_dims_t*, const jampr_instances_t*, const ja
 int jampr_policy_step_tc2(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, const jampr_state_t*,
                           int, int, int, uint64_t, const float*, int, cudaStream_t);
 int64_t jampr_w16_elems(void);
+int jampr_tc_prepare(const jampr_dims_t*, const jampr_instances_t*, int, cudaStream_t);
 
 // Tensor-core policy step: the two-CTAs-per-SM tiling (policy_tc2.cu) when the graph fits it, else the one-CTA
 // tiling (policy_tc.cu).  JAMPR_TC_VARIANT=1 forces the latter (A/B measurements).
@@ -63,6 +64,10 @@ extern "C" int jampr_node_encoder(const jampr_dims_t* d, const jampr_instances_t
   if (rc) return rc;
   // once per episode and < 1 % of it: every precision runs the fp32 kernel, the tensor-core step kernel
   // converts h0 / static_emb on the fly
+  if (w->precision != JAMPR_PREC_F32) {
+    const int rc2 = jampr_tc_prepare(d, inst, w->precision, (cudaStream_t)stream);
+    if (rc2) return rc2;
+  }
   return jampr_node_encoder_f32(d, inst, w->blob, (cudaStream_t)stream);
 }
 

@@ -178,6 +178,7 @@ class RPEnv:
         self.ordered_idx = None
         self._knn = self._knn_w = None
         self._static_emb = self._h0 = None
+        self._tc_tab = self._tc_dtab = None
         self._inst_status = None
         self._dims = None
         self._inst = None
@@ -248,6 +249,9 @@ class RPEnv:
             self._inst_status = torch.zeros(I, dtype=torch.int32, device=dev)
             self._static_emb = torch.empty(I, N, 256, dtype=torch.float32, device=dev)
             self._h0 = torch.empty(I, N, 128, dtype=torch.float32, device=dev)
+            # packed edge tables of the tensor-core policy step (filled by jampr_node_encoder)
+            self._tc_tab = torch.zeros(I, N, (k + 3) // 4 * 4, dtype=torch.int32, device=dev)
+            self._tc_dtab = torch.zeros(I, (N + 7) // 8 * 8, dtype=torch.int32, device=dev)
             self._table_key = shape_key
         self.bs = I * self._num_samples
         self._dims = _cabi.Dims(I, self._num_samples, N, K, k, self.max_vehicle_number, min(64, N),
@@ -257,7 +261,8 @@ class RPEnv:
                         ("service", self.service_time), ("horizon", self.org_service_horizon),
                         ("dist", self._dist_mat), ("ttd", self.time_to_depot), ("knn", self._knn),
                         ("knn_w", self._knn_w), ("order", self.ordered_idx), ("inst_status", self._inst_status),
-                        ("static_emb", self._static_emb), ("h0", self._h0)):
+                        ("static_emb", self._static_emb), ("h0", self._h0), ("tc_tab", self._tc_tab),
+                        ("tc_dtab", self._tc_dtab)):
             setattr(p, name, _cabi.ptr(t))
         given = None
         if dist_mat is not None:

@@ -15,16 +15,16 @@ def num(x):
 def main(path, src):
     lines = open(src).read().split("\n")
     marks = []
-    pats = [("gelu/helpers", r"^__device__ __forceinline__ float rcp_approx"), ("mma/loadw", r"^// ---- one K-block"),
-            ("agg", r"^// ---- max aggregation into"), ("epilogue", r"^// ---- layer epilogue"),
-            ("matvec", r"^// ---- decoder mat-vec"), ("warp_sum4", r"^// sum over the warp of four"),
+    pats = [("mma/loadw", r"void load_w2?\("),
+            ("agg", r"void agg_nbh_tc2?\("), ("epilogue", r"^// y = GELU|^// ---- layer epilogue"),
+            ("matvec", r"^// -* ?decoder mat-vec"), 
             ("kernel head/carve", r"^__global__ void"), ("prologue", r"// -+ prologue"), ("h0", r"// ---- h_0 ="),
-            ("layer loop", r"for \(int l = 0; l < 6"), ("outproj issue", r"// ---- node_emb_output_proj"),
-            ("tour mean", r"// -+ per-tour mean"), ("ne epilogue", r"// -+ node embedding rows"),
+            ("layer loop", r"for \(int l = 0; l < [67]"), 
+            ("ne epilogue", r"// -+ node embedding rows"),
             ("dec b/a te,stats", r"// -+ decoder$"), ("dec c ctxt", r"// \(c\)"), ("dec d qp", r"// \(d\)"),
             ("dec e scores", r"// \(e\)"), ("dec f softmax/pn", r"// \(f\)"), ("dec g gbar", r"// \(g\)"),
             ("dec h g", r"// \(h\)"), ("dec i lp", r"// \(i\)"), ("dec j logits", r"// \(j\)"),
-            ("select", r"// ---- log-softmax"), ("host", r"^static size_t pt_smem_bytes")]
+            ("select", r"// ---- log-softmax"), ("host", r"^static size_t p[t2]_smem_bytes")]
     for name, pat in pats:
         for i, l in enumerate(lines):
             if re.search(pat, l):
@@ -50,7 +50,7 @@ def main(path, src):
                     st_tot[s] += num(r[idx[s]])
             continue
         key = cur
-        if cur == "policy_tc.cu":
+        if cur == src.split("/")[-1]:
             ln = num(r[0])
             key = "?"
             for a, name in marks:
