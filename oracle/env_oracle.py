@@ -240,6 +240,84 @@ class OracleEnv:
         self.done = done
         return cost, done
 
+    # ------------------------------------------------------------------ solution import (LNS repair step)
+    def import_sol(self, sol: List[List], cost: Optional[List] = None) -> None:
+        """Restates RPEnv.import_sol (env.py:575-706) for POMO-style input (one solution per sample): complete
+        tours [0, ..., 0] fill finished plan rows, other tours of length > 1 become active vehicles with
+        recomputed capacity / clock (env.py:708-718, which charges a service at every list element, the depot
+        entries of complete tours included), singletons are dropped; remaining slots get fresh vehicles in the
+        first free rows; the total is the sum of the recomputed tour times when no cost is given; the step
+        counter becomes max_b(visited + finished); the tour-graph refresh rule is evaluated with the step
+        counter of the PREVIOUS episode (env.py:700 runs before :704)."""
+        assert len(sol) == self.I and all(len(s) == self.P for s in sol), "one solution per sample expected"
+        prev_step = self.step_no
+        bs, N, K = self.bs, self.N, self.K
+        self.visited = torch.zeros(bs, N, dtype=torch.bool)
+        self.finished = torch.zeros(bs, self.K_max, dtype=torch.bool)
+        self.active = torch.zeros(bs, self.K_max, dtype=torch.bool)
+        self.plan = torch.zeros(bs, self.K_max, self.L, dtype=torch.int16)
+        self.nxt = torch.zeros(bs, K, dtype=torch.long)
+        self.cur = torch.zeros(bs, K, dtype=torch.long)
+        self.cap = torch.ones(bs, K)
+        self.time = torch.zeros(bs, K)
+        self.cttd = torch.zeros(bs, K)
+        self.row = torch.zeros(bs, K, dtype=torch.long)
+        self.row_last = torch.zeros(bs, K, dtype=torch.long)
+        self.status = torch.zeros(bs, dtype=torch.int32)
+        totals = []
+
+        def recompute(tour, i):
+            tm = torch.zeros((), dtype=torch.float32)
+            prev = 0
+            for n in tour:
+                tm = tm + self.dist[i, prev, n]
+                tm = tm + ((self.tw[i, n, 0] - tm).clamp(min=0) + self.service[i])
+                prev = n
+            return float(tm)
+
+        b = 0
+        for i, inst_sol in enumerate(sol):
+            for smp in inst_sol:
+                num_partial, t_idx, costs = 0, 0, []
+                for tour in smp:
+                    if len(tour) <= 1:
+                        continue
+                    if t_idx >= self.K_max:
+                        raise RuntimeError("Number of tours of provided solution is larger than max_num_vehicles!")
+                    if tour[0] == 0 and tour[-1] == 0:
+                        self.plan[b, t_idx, : len(tour) - 1] = torch.tensor(tour[1:], dtype=torch.int16)
+                        self.finished[b, t_idx] = True
+                        costs.append(recompute(tour, i))
+                    else:
+                        t = torch.tensor(tour, dtype=torch.long)
+                        self.plan[b, t_idx, : len(tour)] = t.to(torch.int16)
+                        self.cur[b, num_partial] = t[-1]
+                        self.cap[b, num_partial] = 1.0 - self.demand[i].gather(0, t).sum()
+                        self.cttd[b, num_partial] = self.ttd[i, t[-1]]
+                        tm = recompute(tour, i)
+                        costs.append(tm)
+                        self.time[b, num_partial] = tm
+                        self.nxt[b, num_partial] = len(tour)
+                        self.active[b, t_idx] = True
+                        self.row_last[b, num_partial] = t[-1]
+                        num_partial += 1
+                    t_idx += 1
+                assert num_partial <= K
+                for _ in range(num_partial, K):
+                    nf = int(torch.argmin((self.finished[b] | self.active[b]).to(torch.int)))
+                    self.active[b, nf] = True
+                self.row[b] = self.active[b].nonzero().view(-1)          # env.py:697: ascending plan rows
+                nz = self.plan[b][self.plan[b] > 0].long()
+                self.visited[b, nz] = True
+                totals.append(sum(costs))
+                b += 1
+        self.total = torch.tensor(totals, dtype=torch.float32) if cost is None else \
+            torch.tensor(cost, dtype=torch.float32).view(-1)
+        self.pred, self.succ = self.links_from_plan()
+        self.graph_fresh = (prev_step <= K + 1) or (prev_step % self.upd == 0)
+        self.step_no = int((self.visited.sum(-1) + self.finished.sum(-1)).max())
+        self.done = False
+
     # ------------------------------------------------------------------ observation
     def observe(self):
         """Candidate sets nbh (bs, K, k) and infeasibility mask (bs, K, k)."""

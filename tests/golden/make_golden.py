@@ -125,7 +125,91 @@ def run_case(name, instances, env_kwargs, decode="greedy", seed=1235, policy_see
     return out
 
 
+def run_repair_case(name, instances, env_kwargs, seed=1235, policy_seed=0, destroy_seed=5):
+    """LNS repair step (lns.py:236-275 with construct -> destroy -> import_sol -> re-rollout): a greedy POMO
+    construction, a seeded destroy in the manner of env.py:_test_io (the K longest tours of every sample are cut
+    to a random prefix and stay open, the rest stay complete), RPEnv.import_sol, then the recorded repair rollout."""
+    pol = build_policy(policy_seed)
+    pol.set_decode_type("greedy")
+    pol.reset_static()
+    env = RPEnv(inference=True, **env_kwargs)
+    env.seed(seed)
+    env.load_data(to_ref(instances))
+    obs = env.reset()
+    done = False
+    with torch.no_grad():
+        while not done:
+            action, _, _ = pol(obs)
+            obs, _, done, _ = env.step(action)
+    prev_step = int(env._step)
+    K, P = env.max_concurrent_vehicles, env.num_samples
+    rng = np.random.default_rng(destroy_seed)
+    plan = env.tour_plan.numpy().reshape(-1, P, *env.tour_plan.shape[1:])
+    sol = []
+    for inst_plan in plan:
+        inst_sol = []
+        for smp in inst_plan:
+            tours = [r[r > 0].tolist() for r in smp if (r > 0).any()]
+            order = np.argsort([-len(t) for t in tours], kind="stable")
+            new = []
+            for rank, ti in enumerate(order):
+                t = tours[ti]
+                if rank < K:
+                    tlim = int(rng.integers(2, max(len(t) - 1, 3)))
+                    new.append([int(x) for x in t[:tlim]])
+                else:
+                    new.append([0] + [int(x) for x in t] + [0])
+            inst_sol.append(new)
+        sol.append(inst_sol)
+    # the reference needs a loaded instance for import_sol
+    env.load_data(to_ref(instances))
+    logp_box = {}
+    pol.decoder.register_forward_hook(lambda m, i, o: logp_box.__setitem__("v", o.detach().clone()))
+    obs = env.import_sol(sol)
+    out = {f"inst_{k}": v for k, v in instances_to_arrays(instances).items()}
+    out["static_dist"] = env._dist_mat.view(-1, P, env.graph_size, env.graph_size)[:, 0].numpy().copy()
+    out["static_k_max"] = np.int64(env.max_vehicle_number)
+    out["import_total"] = env.total_cost.numpy().copy()
+    out["import_step"] = np.int64(env._step)
+    out["import_plan"] = env.tour_plan.numpy().copy()
+    out["import_rows"] = env.active_to_plan_idx.numpy().copy()
+    out["import_visited"] = env._visited.numpy().copy()
+    out["prev_step"] = np.int64(prev_step)
+    out["solution_json"] = np.array(json.dumps(sol))
+    trace = {k: [] for k in ("nbh", "mask", "tour_features", "logp", "action", "cost", "n_tour_edges", "total")}
+    done = False
+    with torch.no_grad():
+        while not done:
+            action, ll, ent = pol(obs)
+            trace["nbh"].append(obs.nbh.numpy().astype(np.int16))
+            trace["mask"].append(obs.nbh_mask.numpy().copy())
+            trace["tour_features"].append(obs.tour_features.numpy().copy())
+            trace["logp"].append(logp_box["v"].numpy().copy())
+            trace["n_tour_edges"].append(np.int64(obs.tour_edges.numel() // 2 if obs.tour_edges.dim() == 2 else -1))
+            trace["action"].append(action.numpy().astype(np.int16))
+            obs, cost, done, info = env.step(action)
+            trace["cost"].append(cost.numpy().copy())
+            trace["total"].append(env.total_cost.numpy().copy())
+    out.update({f"trace_{k}": np.stack(v) for k, v in trace.items()})
+    out["final_tour_plan"] = env.tour_plan.numpy().copy()
+    out["final_total_cost"] = env.total_cost.numpy().copy()
+    out["final_visited"] = env._visited.numpy().copy()
+    out["final_step"] = np.int64(env._step)
+    out["env_kwargs"] = np.array(json.dumps(env_kwargs))
+    out["decode"] = np.array("greedy")
+    out["policy_seed"] = np.int64(policy_seed)
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: construct ended at step {prev_step}; import -> step {int(out['import_step'])}, "
+          f"repair steps={len(trace['action'])}, final_step={env._step} -> {os.path.getsize(path)/1e6:.2f} MB")
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "repair":
+        run_repair_case("g51_repair", sample_instances(3, graph_size=50, seed=21),
+                        dict(max_concurrent_vehicles=3, k_nbh_frac=0.25, pomo=True, num_samples=6))
+        return
     with open(os.path.join(HERE, "state_dict_schema.json"), "w") as f:
         json.dump({k: list(v) for k, v in state_dict_schema().items()}, f, indent=1)
 
@@ -156,6 +240,10 @@ def main():
     run_case("g31_k2", sample_instances(4, graph_size=30, seed=17),
              dict(max_concurrent_vehicles=2, k_nbh_frac=0.4, pomo=True, pomo_nbh_frac=0.5, num_samples=4),
              policy_seed=3)
+
+    # case 6: the LNS repair step: construct -> destroy -> import_sol -> repair rollout
+    run_repair_case("g51_repair", sample_instances(3, graph_size=50, seed=21),
+                    dict(max_concurrent_vehicles=3, k_nbh_frac=0.25, pomo=True, num_samples=6))
 
 
 if __name__ == "__main__":

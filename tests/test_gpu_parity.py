@@ -326,3 +326,43 @@ def test_export_import_roundtrip_keeps_tours():
         rows = [r[r > 0].tolist() for r in plan0[b].cpu().numpy() if (r > 0).any()]
         got = [r[r > 0].tolist() for r in env.tour_plan[b].cpu().numpy() if (r > 0).any()]
         assert rows == got
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_repair_step_import_sol(precision):
+    """LNS repair step on the device: RPEnv.import_sol (env.py:575-706) and the repair rollout against the
+    reference trace (construct -> seeded destroy -> import_sol -> greedy repair).  Environment side bit-exact for
+    both policy precisions; log-probs to the fp32 bar, or to the tensor-core bar of test_gpu_tc_policy."""
+    import json
+    g = load_case("g51_repair")
+    env, pol = _make(g, precision=precision)
+    env.reset()
+    env._step = int(g["prev_step"])                    # the construction episode that preceded the import
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        obs = env.import_sol(json.loads(str(g["solution_json"])))
+        assert np.array_equal(env.tour_plan.cpu().numpy(), g["import_plan"])
+        assert np.array_equal(env.active_to_plan_idx.cpu().numpy(), g["import_rows"])
+        assert np.array_equal(env._visited.cpu().numpy(), g["import_visited"])
+        assert np.array_equal(env.total_cost.cpu().numpy(), g["import_total"])
+        assert env._step == int(g["import_step"])
+        T = g["trace_action"].shape[0]
+        atol = LOGP_ATOL if precision == "fp32" else 2.5e-2
+        for t in range(T):
+            assert np.array_equal(obs.nbh.cpu().numpy(), g["trace_nbh"][t]), f"nbh step {t}"
+            assert np.array_equal(obs.nbh_mask.cpu().numpy(), g["trace_mask"][t]), f"mask step {t}"
+            assert env._graph_fresh == (int(g["trace_n_tour_edges"][t]) >= 0), f"graph refresh rule step {t}"
+            pol(obs)
+            logp = pol.log_probs(env).cpu().numpy()
+            ref = g["trace_logp"][t]
+            fin = np.isfinite(ref)
+            assert np.array_equal(np.isfinite(logp), fin), f"support step {t}"
+            assert (np.abs(logp[fin] - ref[fin]) <= atol + LOGP_RTOL * np.abs(ref[fin])).all(), t
+            obs, cost, done, _ = env.step(torch.from_numpy(g["trace_action"][t].astype(np.int64)))
+            if not done:
+                assert np.array_equal(cost.cpu().numpy(), g["trace_cost"][t]), f"cost step {t}"
+                assert np.array_equal(env.total_cost.cpu().numpy(), g["trace_total"][t]), f"total step {t}"
+    assert done
+    assert np.array_equal(env.tour_plan.cpu().numpy(), g["final_tour_plan"])
+    np.testing.assert_allclose(env.total_cost.cpu().numpy(), g["final_total_cost"], rtol=FINAL_COST_RTOL, atol=0)
+    assert env._step == int(g["final_step"])

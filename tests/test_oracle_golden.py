@@ -88,3 +88,41 @@ def test_node_encoder_matches_reference():
     env, pol = make_oracle(g)
     emb = pol.encode_nodes(env)[0].numpy()
     assert np.abs(emb - g["static_node_emb0"]).max() <= 2e-5
+
+
+def test_repair_step_import_sol():
+    """LNS repair step: the oracle's import_sol (env.py:575-706) and the repair rollout that follows, against the
+    reference trace (construct -> seeded destroy -> import_sol -> greedy repair, tests/golden/make_golden.py)."""
+    import json
+    g = load_case("g51_repair")
+    env, pol = make_oracle(g)
+    env.reset(start_nodes=None if not env.pomo else torch.zeros(env.bs, env.K, dtype=torch.long) + 1)
+    env.step_no = int(g["prev_step"])                 # the construction episode that preceded the import
+    env.import_sol(json.loads(str(g["solution_json"])))
+    assert np.array_equal(env.plan.numpy(), g["import_plan"])
+    assert np.array_equal(env.row.numpy(), g["import_rows"])
+    assert np.array_equal(env.visited.numpy(), g["import_visited"])
+    assert np.array_equal(env.total.numpy(), g["import_total"])
+    assert env.step_no == int(g["import_step"])
+    T = g["trace_action"].shape[0]
+    worst = 0.0
+    for t in range(T):
+        nbh, mask = env.observe()
+        assert np.array_equal(nbh.numpy().astype(np.int16), g["trace_nbh"][t]), f"nbh step {t}"
+        assert np.array_equal(mask.numpy(), g["trace_mask"][t]), f"mask step {t}"
+        assert np.array_equal(env.tour_features().numpy(), g["trace_tour_features"][t]), f"tour features step {t}"
+        assert env.graph_fresh == (int(g["trace_n_tour_edges"][t]) >= 0), f"graph refresh rule step {t}"
+        logp = pol.forward(env, nbh, mask).numpy()
+        ref = g["trace_logp"][t]
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(logp), fin)
+        worst = max(worst, float(np.abs(logp[fin] - ref[fin]).max()))
+        cost, done = env.step(torch.from_numpy(g["trace_action"][t].astype(np.int64)))
+        if not done:
+            assert np.array_equal(cost.numpy(), g["trace_cost"][t]), f"cost step {t}"
+            assert np.array_equal(env.total.numpy(), g["trace_total"][t]), f"total step {t}"
+        else:
+            np.testing.assert_allclose(env.total.numpy(), g["trace_total"][t], rtol=1e-6)
+    assert done and worst <= LOGP_ATOL, worst
+    assert np.array_equal(env.plan.numpy(), g["final_tour_plan"])
+    assert env.step_no == int(g["final_step"])
