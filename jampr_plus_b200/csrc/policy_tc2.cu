@@ -15,7 +15,7 @@
 
 #define P2_THREADS 256
 #define P2_WARPS (P2_THREADS / 32)
-#define P2_GROUPS ((P2_THREADS - 32) / 16)   // customer rows aggregated concurrently (warps 1..7)
+#define P2_GROUPS ((P2_THREADS - 32) / 8)    // customer rows aggregated concurrently (warps 1..7, 8 threads per row)
 #define NE16_STRIDE 528                       // bytes per parked node-embedding row: 256 x 16 bit + 16 (bank shift 4 words)
 #define QP2_STRIDE 260
 
@@ -42,11 +42,16 @@ __device__ __forceinline__ void agg_nbh_tc2(uint8_t* sA, uint32_t ts, uint32_t t
     r.w = as_u32(__hmax2(from_u32<T2>(r.w), from_u32<T2>(__shfl_xor_sync(0xffffffffu, r.w, 16))));
     if (half == 0) *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = r;
   } else {
-    const int g = (tid - 32) >> 4, cc = (tid - 32) & 15;
-    const uint32_t kboff = (uint32_t)(cc >> 3) * ts, c = cc & 7;
+    // 8 threads per customer row, two adjacent 16-byte chunks each (chunk pair cp of K-block cp >> 2)
+    const int g = (tid - 32) >> 3, cp = (tid - 32) & 7;
+    // chunks (c, c ^ 4); the K-block-1 threads start with the upper chunk so that the eight threads of a row hit
+    // eight distinct 16-byte bank groups in each of their two loads
+    const uint32_t kboff = (uint32_t)(cp >> 2) * ts, cA = (uint32_t)(cp & 3) + (uint32_t)(cp >> 2) * 4u, cB = cA ^ 4u;
     for (int u = 1 + g; u < N; u += P2_GROUPS) {
-      const uint4 r = agg_run<T>(tab_saddr + (uint32_t)(u * k4) * 4u, 0, k4, h_saddr + kboff, c << 4);
-      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, c)) = r;
+      uint4 ra, rb;
+      agg_run2<T>(tab_saddr + (uint32_t)(u * k4) * 4u, 0, k4, h_saddr + kboff, cA << 4, cB << 4, ra, rb);
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, cA)) = ra;
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, cB)) = rb;
     }
   }
 }
@@ -65,12 +70,15 @@ __device__ __forceinline__ void agg_tour_tc2(uint8_t* sA, uint32_t ts, const uin
       *reinterpret_cast<uint4*>(sA + kboff + sw128_off(0, c)) = r;
     }
   } else {
-    const int g = (tid - 32) >> 4, cc = (tid - 32) & 15;
-    const uint32_t kboff = (uint32_t)(cc >> 3) * ts, c = cc & 7;
+    const int g = (tid - 32) >> 3, cp = (tid - 32) & 7;
+    // chunks (c, c ^ 4); the K-block-1 threads start with the upper chunk so that the eight threads of a row hit
+    // eight distinct 16-byte bank groups in each of their two loads
+    const uint32_t kboff = (uint32_t)(cp >> 2) * ts, cA = (uint32_t)(cp & 3) + (uint32_t)(cp >> 2) * 4u, cB = cA ^ 4u;
     for (int u = 1 + g; u < N; u += P2_GROUPS) {
-      T2 m[4];
-      agg_edge<T>(s_ltab[u], h_saddr + kboff, c << 4, m, true);
-      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, c)) = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
+      T2 m[8];
+      agg_edge2<T>(s_ltab[u], h_saddr + kboff, cA << 4, cB << 4, m, true);
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, cA)) = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
+      *reinterpret_cast<uint4*>(sA + kboff + sw128_off(u, cB)) = make_uint4(as_u32(m[4]), as_u32(m[5]), as_u32(m[6]), as_u32(m[7]));
     }
   }
 }
@@ -506,24 +514,36 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       __syncthreads();
       tc_fence_after();
     }
-    // ---- node embedding rows: ne = acc + b + static_emb -> parked 16-bit rows (+ fp32 to HBM when cached)
+    // ---- node embedding rows: ne = acc + b + static_emb -> parked 16-bit rows (+ fp32 to HBM when cached).
+    // The static_emb rows come from L2: chunk c+1 is in flight while chunk c is combined; chunk 0 is requested
+    // before the wait for the projection MMAs.
+    const float4* se_row = reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + min(r, N - 1)) * 256 + ch * 128);
+    float4 sv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sv[i] = __ldg(se_row + i);
     if (tid == 0) mbar_wait(bar_acc, 0u);
     __syncthreads();          // projection complete and per-tour means done: the h tiles may be overwritten
     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int col0 = ch * 128 + c * 32;
       uint32_t acc[32];
       tmem_ld32_nowait(ta + col0, acc);
+      float4 cur[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = sv[i];
+      if (c < 3) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sv[i] = __ldg(se_row + (c + 1) * 8 + i);
+      }
       tmem_wait_ld();
       if (r < N) {
-        const float4* se = reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + r) * 256 + col0);
         const float4* bo = reinterpret_cast<const float4*>(w + OFF_TE_OUT_B + col0);
         float4* gdst = a.store_cache ? reinterpret_cast<float4*>(st.ne + ((size_t)b * N + r) * 256 + col0) : nullptr;
         uint8_t* dst = s_ne16 + (size_t)r * NE16_STRIDE + col0 * 2;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 sa = __ldg(se + 2 * i), sb = __ldg(se + 2 * i + 1), ba = __ldg(bo + 2 * i), bb = __ldg(bo + 2 * i + 1);
+          const float4 sa = cur[2 * i], sb = cur[2 * i + 1], ba = __ldg(bo + 2 * i), bb = __ldg(bo + 2 * i + 1);
           const float4 va = make_float4(__uint_as_float(acc[8 * i]) + ba.x + sa.x, __uint_as_float(acc[8 * i + 1]) + ba.y + sa.y,
                                         __uint_as_float(acc[8 * i + 2]) + ba.z + sa.z, __uint_as_float(acc[8 * i + 3]) + ba.w + sa.w);
           const float4 vb = make_float4(__uint_as_float(acc[8 * i + 4]) + bb.x + sb.x, __uint_as_float(acc[8 * i + 5]) + bb.y + sb.y,

@@ -140,6 +140,42 @@ __device__ __forceinline__ uint4 agg_run(uint32_t tab_saddr, int e0, int e1, uin
   return make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
 }
 
+// two adjacent 16-byte chunks (cA, cB = chunk index << 4) of the same rows per thread: the edge decode (offset,
+// weight broadcast, table load) is paid once for 32 bytes of features
+template <typename T>
+__device__ __forceinline__ void agg_edge2(uint32_t e, uint32_t hb, uint32_t cA, uint32_t cB, typename Elem<T>::T2 (&m)[8],
+                                          bool first) {
+  using T2 = typename Elem<T>::T2;
+  const T2 w2 = from_u32<T2>(__byte_perm(e, e, 0x3232));
+  const uint32_t ro = e & 0xffffu;
+  const uint4 va = lds128(hb + (ro ^ cA)), vb = lds128(hb + (ro ^ cB));
+  const T2 p0 = __hmul2(from_u32<T2>(va.x), w2), p1 = __hmul2(from_u32<T2>(va.y), w2);
+  const T2 p2 = __hmul2(from_u32<T2>(va.z), w2), p3 = __hmul2(from_u32<T2>(va.w), w2);
+  const T2 p4 = __hmul2(from_u32<T2>(vb.x), w2), p5 = __hmul2(from_u32<T2>(vb.y), w2);
+  const T2 p6 = __hmul2(from_u32<T2>(vb.z), w2), p7 = __hmul2(from_u32<T2>(vb.w), w2);
+  if (first) { m[0] = p0; m[1] = p1; m[2] = p2; m[3] = p3; m[4] = p4; m[5] = p5; m[6] = p6; m[7] = p7; }
+  else {
+    m[0] = __hmax2(m[0], p0); m[1] = __hmax2(m[1], p1); m[2] = __hmax2(m[2], p2); m[3] = __hmax2(m[3], p3);
+    m[4] = __hmax2(m[4], p4); m[5] = __hmax2(m[5], p5); m[6] = __hmax2(m[6], p6); m[7] = __hmax2(m[7], p7);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void agg_run2(uint32_t tab_saddr, int e0, int e1, uint32_t hb, uint32_t cA, uint32_t cB,
+                                         uint4& ra, uint4& rb) {
+  using T2 = typename Elem<T>::T2;
+  T2 m[8];
+  for (int j = e0; j < e1; j += 4) {
+    const uint4 q = lds128(tab_saddr + (uint32_t)j * 4u);
+    agg_edge2<T>(q.x, hb, cA, cB, m, j == e0);
+    agg_edge2<T>(q.y, hb, cA, cB, m, false);
+    agg_edge2<T>(q.z, hb, cA, cB, m, false);
+    agg_edge2<T>(q.w, hb, cA, cB, m, false);
+  }
+  ra = make_uint4(as_u32(m[0]), as_u32(m[1]), as_u32(m[2]), as_u32(m[3]));
+  rb = make_uint4(as_u32(m[4]), as_u32(m[5]), as_u32(m[6]), as_u32(m[7]));
+}
+
 // sum over the warp of four values at once: lane 16*(h>>1) + 8*(h&1) ends up with the total of value h
 __device__ __forceinline__ float warp_sum4(float d0, float d1, float d2, float d3, int lane) {
   const bool up4 = (lane & 16) != 0, up3 = (lane & 8) != 0;
