@@ -825,6 +825,7 @@ int jampr_policy_step_tc(const jampr_dims_t* d, const jampr_instances_t* inst, c
   a.decode_type = decode_type;
   a.graph_fresh = graph_fresh;
   a.store_cache = store_cache;
+  a.ablate = 0;
   if (w->precision == JAMPR_PREC_F16) return launch_pt<__half>(a, smem, s);
   return launch_pt<__nv_bfloat16>(a, smem, s);
 }

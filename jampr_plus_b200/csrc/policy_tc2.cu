@@ -11,6 +11,7 @@
 //   * layer epilogue in two passes over the thread's 64 accumulator columns (pass 1 parks GELU + skip back into the
 //     accumulator columns of TMEM and reduces the LayerNorm statistics, pass 2 normalises).
 // One CTA = one rollout = one step.  See policy_tc.cu for the single-CTA-per-SM variant with fp32 parked embeddings.
+#include <stdlib.h>
 #include "policy_tc_common.cuh"
 
 #define P2_THREADS 256
@@ -448,8 +449,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         mbar_wait(&full[0], 0u);
         mbar_wait(&full[1], 0u);
         tc_fence_after();
-        mma_kblock(tmem, a_addr + 2 * ts, w_addr, idesc, true);
-        mma_kblock(tmem, a_addr + 3 * ts, w_addr + 16384, idesc, false);
+        if (!(a.ablate & 8)) {
+          mma_kblock(tmem, a_addr + 2 * ts, w_addr, idesc, true);
+          mma_kblock(tmem, a_addr + 3 * ts, w_addr + 16384, idesc, false);
+        }
         umma_commit(bar_root);
         mbar_wait(bar_root, ph);                     // both stages free again: stream the second pair
         load_w2<T>(sW, 0, a.w16, l * 4 + (proj ? 2 : 0), full);
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         if (tid >= 32 && tid < 128)
           reinterpret_cast<float4*>(s_par)[tid - 32] =
               __ldg(reinterpret_cast<const float4*>(w + OFF_TE_BLK + (size_t)l * BLK_FLOATS + BLK_B) + (tid - 32));
-        if (l == 2 || l == 5) agg_nbh_tc2<T>(sA, ts, tab_saddr, k4, dtab_saddr, nd, N);
+        if (l == 2 || l == 5) { if (!(a.ablate & 1)) agg_nbh_tc2<T>(sA, ts, tab_saddr, k4, dtab_saddr, nd, N); }
         else if (l < 2) agg_tour_tc2<T>(sA, ts, s_lf, ef_saddr, n_ef4, N);
         else agg_tour_tc2<T>(sA, ts, s_lr, er_saddr, n_er4, N);
         fence_proxy_async();
@@ -489,7 +492,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         mbar_wait(&full[0], 1u);
         mbar_wait(&full[1], 1u);
         tc_fence_after();
-        if (!proj) {
+        if (a.ablate & 8) {
+        } else if (!proj) {
           mma_kblock(tmem, a_addr, w_addr, idesc, false);                   // lin_rel(agg): K-blocks 0,1
           mma_kblock(tmem, a_addr + ts, w_addr + 16384, idesc, false);
         } else {
@@ -507,8 +511,9 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       }
       __syncthreads();
       tc_fence_after();
-      layer_epilogue2<T>(tmem, sA, ts, s_red, par_saddr, N,
-                         (l == 5 && a.store_cache) ? st.h_fin + (size_t)b * N * 128 : nullptr);
+      if (!(a.ablate & 2))
+        layer_epilogue2<T>(tmem, sA, ts, s_red, par_saddr, N,
+                           (l == 5 && a.store_cache) ? st.h_fin + (size_t)b * N * 128 : nullptr);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -584,7 +589,19 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   // ---------------------------------------------------------------- decoder
   const uint32_t ne_saddr = smem_u32(s_ne16), te_saddr = smem_u32(s_te);
   // (b) tour_emb[t] = folded tour-feature branch + W_to2 mean_h[t]          (tour_encoder.py:202-213)
-  matvec2<T, 2, 4>(w16 + W16_TO2, 128, smem_u32(s_mean), 128, s_part);     // NV = 4 >= K slots (K <= 4 here)
+  const bool mv = !(a.ablate & 4);
+  if (a.ablate & 16) {      // timing experiment: first feasible action, nothing else
+    if (tid == 0) {
+      int choice = 0;
+      for (int e = 0; e < A; ++e) if (!s_mask[e]) { choice = e; break; }
+      st.action[2 * (size_t)b] = choice / k;
+      st.action[2 * (size_t)b + 1] = s_nbh[choice];
+      st.ll[b] = 0.0f;
+      st.entropy[b] = 0.0f;
+    }
+    return;
+  }
+  if (mv) matvec2<T, 2, 4>(w16 + W16_TO2, 128, smem_u32(s_mean), 128, s_part);     // NV = 4 >= K slots (K <= 4 here)
   // (a) column mean / max of node_emb over the nodes (policy.py:179-181): thread = column pair x row parity
   {
     const int c2 = tid & 127, half = tid >> 7;
@@ -620,7 +637,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   __syncthreads();
   // (c) ctxt = ctxt_proj(query)
-  matvec2<T, 8, 1>(w16 + W16_CTXT, 512, smem_u32(s_q), 0, s_part);
+  if (mv) matvec2<T, 8, 1>(w16 + W16_CTXT, 512, smem_u32(s_q), 0, s_part);
   __syncthreads();
   {
     float v = 0.0f;
@@ -630,7 +647,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   __syncthreads();
   // (d) qp[h] = W_gk,h^T ctxt_h : K-slice ks (32 rows of set_proj) belongs to head ks / 2
-  matvec2<T, 8, 1>(w16 + W16_GK, 256, smem_u32(s_ctxt), 0, s_part);
+  if (mv) matvec2<T, 8, 1>(w16 + W16_GK, 256, smem_u32(s_ctxt), 0, s_part);
   __syncthreads();
   for (int e = tid; e < 1024; e += P2_THREADS) {
     const int h = e >> 8, c = e & 255;
@@ -739,7 +756,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   __syncthreads();
   // (h) glimpse g[o] = W_gv[o] . gbar[head(o)]
-  matvec2<T, 8, 1>(w16 + W16_GV, 256, smem_u32(s_gbar) + (uint32_t)((tid & 31) >> 3) * QP2_STRIDE * 4u, 0, s_part);
+  if (mv) matvec2<T, 8, 1>(w16 + W16_GV, 256, smem_u32(s_gbar) + (uint32_t)((tid & 31) >> 3) * QP2_STRIDE * 4u, 0, s_part);
   __syncthreads();
   {
     float v = 0.0f;
@@ -749,7 +766,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   __syncthreads();
   // (i) lp = W_lk^T out_proj(g) = M1 g
-  matvec2<T, 8, 1>(w16 + W16_M1, 256, smem_u32(s_g), 0, s_part);
+  if (mv) matvec2<T, 8, 1>(w16 + W16_M1, 256, smem_u32(s_g), 0, s_part);
   __syncthreads();
   {
     float v = 0.0f;
@@ -890,6 +907,11 @@ int jampr_policy_step_tc2(const jampr_dims_t* d, const jampr_instances_t* inst, 
   a.decode_type = decode_type;
   a.graph_fresh = graph_fresh;
   a.store_cache = store_cache;
+  static const int ablate = [] {
+    const char* e = getenv("JAMPR_TC_ABLATE");
+    return e ? atoi(e) : 0;
+  }();
+  a.ablate = ablate;
   if (w->precision == JAMPR_PREC_F16) return launch_p2<__half>(a, smem, s);
   return launch_p2<__nv_bfloat16>(a, smem, s);
 }

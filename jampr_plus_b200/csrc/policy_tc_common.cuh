@@ -27,6 +27,8 @@ struct PtArgs {
   int decode_type;
   int graph_fresh;
   int store_cache;       // write h_fin / ne / ne_stats to HBM (needed when later steps reuse them)
+  int ablate;            // timing experiments only (JAMPR_TC_ABLATE): 1 skip kNN aggregation, 2 skip layer epilogue
+                         // math, 4 skip the decoder mat-vec chain, 8 skip the MMAs, 16 skip the whole decoder
 };
 
 template <typename T>
