@@ -14,6 +14,13 @@
 #include <stdlib.h>
 #include "policy_tc_common.cuh"
 
+// timing experiments (tools/ablate.sh): build with `make EXTRA=-DJAMPR_ABLATE_BUILD`, select with JAMPR_TC_ABLATE
+#ifdef JAMPR_ABLATE_BUILD
+#define ABL(bit) ((a.ablate & (bit)) != 0)
+#else
+#define ABL(bit) false
+#endif
+
 #define P2_THREADS 256
 #define P2_WARPS (P2_THREADS / 32)
 #define P2_GROUPS ((P2_THREADS - 32) / 8)    // customer rows aggregated concurrently (warps 1..7, 8 threads per row)
@@ -449,7 +456,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         mbar_wait(&full[0], 0u);
         mbar_wait(&full[1], 0u);
         tc_fence_after();
-        if (!(a.ablate & 8)) {
+        if (!(ABL(8))) {
           mma_kblock(tmem, a_addr + 2 * ts, w_addr, idesc, true);
           mma_kblock(tmem, a_addr + 3 * ts, w_addr + 16384, idesc, false);
         }
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         if (tid >= 32 && tid < 128)
           reinterpret_cast<float4*>(s_par)[tid - 32] =
               __ldg(reinterpret_cast<const float4*>(w + OFF_TE_BLK + (size_t)l * BLK_FLOATS + BLK_B) + (tid - 32));
-        if (l == 2 || l == 5) { if (!(a.ablate & 1)) agg_nbh_tc2<T>(sA, ts, tab_saddr, k4, dtab_saddr, nd, N); }
+        if (l == 2 || l == 5) { if (!(ABL(1))) agg_nbh_tc2<T>(sA, ts, tab_saddr, k4, dtab_saddr, nd, N); }
         else if (l < 2) agg_tour_tc2<T>(sA, ts, s_lf, ef_saddr, n_ef4, N);
         else agg_tour_tc2<T>(sA, ts, s_lr, er_saddr, n_er4, N);
         fence_proxy_async();
@@ -492,7 +499,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         mbar_wait(&full[0], 1u);
         mbar_wait(&full[1], 1u);
         tc_fence_after();
-        if (a.ablate & 8) {
+        if (ABL(8)) {
         } else if (!proj) {
           mma_kblock(tmem, a_addr, w_addr, idesc, false);                   // lin_rel(agg): K-blocks 0,1
           mma_kblock(tmem, a_addr + ts, w_addr + 16384, idesc, false);
@@ -511,7 +518,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       }
       __syncthreads();
       tc_fence_after();
-      if (!(a.ablate & 2))
+      if (!(ABL(2)))
         layer_epilogue2<T>(tmem, sA, ts, s_red, par_saddr, N,
                            (l == 5 && a.store_cache) ? st.h_fin + (size_t)b * N * 128 : nullptr);
       fence_proxy_async();
@@ -589,8 +596,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   // ---------------------------------------------------------------- decoder
   const uint32_t ne_saddr = smem_u32(s_ne16), te_saddr = smem_u32(s_te);
   // (b) tour_emb[t] = folded tour-feature branch + W_to2 mean_h[t]          (tour_encoder.py:202-213)
-  const bool mv = !(a.ablate & 4);
-  if (a.ablate & 16) {      // timing experiment: first feasible action, nothing else
+  const bool mv = !(ABL(4));
+  if (ABL(16)) {      // timing experiment: first feasible action, nothing else
     if (tid == 0) {
       int choice = 0;
       for (int e = 0; e < A; ++e) if (!s_mask[e]) { choice = e; break; }
