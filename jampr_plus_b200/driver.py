@@ -14,8 +14,25 @@ from .routing.formats import RPInstance
 __all__ = ["rollout", "eval_episode"]
 
 
-def rollout(policy, env, max_steps: Optional[int] = None, check: bool = True) -> Tuple[torch.Tensor, Dict]:
+_GRAPHS: Dict = {}
+
+
+def _enqueue(policy, env, w, n):
+    st = env.state
+    rc = policy._lib.jampr_rollout(env._dims, env._inst, w, st.struct(), int(env._step), int(env._graph_fresh),
+                                   policy._decode_code(), int(policy.sampling_seed), int(n), env._stream())
+    return _cabi.check(rc, "jampr_rollout")
+
+
+def rollout(policy, env, max_steps: Optional[int] = None, check: bool = True,
+            graph: bool = False) -> Tuple[torch.Tensor, Dict]:
     """Run the episode currently held by ``env`` (after reset() / import_sol()) to termination on the device.
+
+    ``graph=True`` captures the whole multi-step loop (3 kernels per step, ~130 steps) into a CUDA graph the first
+    time a (state buffers, weights, start step, decode type) combination is seen and replays it afterwards: one
+    host call per episode, which is what matters for the small batches of the LNS repair loop (lns.py:236-275).
+    Requires stable buffers: the same env / policy objects and equally shaped batches (RPEnv reuses its device
+    buffers), greedy decoding or a fixed sampling seed.
 
     Returns (total cost (bs,), info) with the reference's info keys."""
     assert env._is_reset, "call env.reset() or env.import_sol() first"
@@ -24,9 +41,25 @@ def rollout(policy, env, max_steps: Optional[int] = None, check: bool = True) ->
     w = policy.encode_static(env)
     cap = env.graph_size + env.max_vehicle_number + 1
     n = cap - env._step + 1 if max_steps is None else max_steps
-    rc = policy._lib.jampr_rollout(env._dims, env._inst, w, st.struct(), int(env._step), int(env._graph_fresh),
-                                   policy._decode_code(), int(policy.sampling_seed), int(n), env._stream())
-    _cabi.check(rc, "jampr_rollout")
+    if graph:
+        key = (id(env), id(policy), tuple(t.data_ptr() for t in st.t.values()), policy._blob.data_ptr(),
+               env.coords.data_ptr(), env._dist_mat.data_ptr(), env.bs, int(env._step), int(env._graph_fresh),
+               policy._decode_code(), int(policy.sampling_seed), int(n), policy.precision)
+        g = _GRAPHS.get(key)
+        if g is None:
+            rc = _enqueue(policy, env, w, n)            # eager first run (also sets the kernels' smem attributes)
+            if len(_GRAPHS) > 64:
+                _GRAPHS.clear()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                  # capture launches nothing: the eager run above is the result
+                rc_cap = _enqueue(policy, env, w, n)
+            assert rc_cap == rc
+            _GRAPHS[key] = (g, rc)
+        else:
+            g[0].replay()
+            rc = g[1]
+    else:
+        rc = _enqueue(policy, env, w, n)
     info: Dict = {}
     if check:
         done_step = int(st["ctl"][_cabi.CTL_DONE_STEP].item())      # the one device->host sync of the rollout

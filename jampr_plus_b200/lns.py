@@ -1,0 +1,196 @@
+"""LNS driver on the B200 construction / repair path: construct -> [select -> destroy -> repair]*.
+
+Mirrors the search loop of reference ``lib/lns/lns.py:236-372`` for the part this repo accelerates: model
+construction (``_construct``, :236-275) on ``RPEnv`` / ``Policy`` / the fused device rollout, selection of
+``num_best + num_other`` samples (``RPEnv.export_sol``), the incumbent bookkeeping (``_select_best`` / ``_add_best``,
+:175-222), the bootstrap of the selected solutions back to ``num_samples`` and their destruction (``_destruct``,
+:296-313 with ``lib/lns/destructor.py:64-205``: random_from_route with random_nodes / random_cut / const_cut and
+random / smallest complete-route removal), ``RPEnv.import_sol`` and the repair rollout.
+
+NOT here: the OR-tools guided local search (``lib/lns/gort.py``; OR-tools is neither installed nor pinned by the
+reference), the ``similarity`` / ``waiting_time`` removal modes (difflib / OR-tools infos) and the DIMACS controller
+protocol.  Costs are reported two ways: the environment's own total (what the reference's loop compares, SURVEY.md
+§0.6 / A.6 explains its quirks) and the batch-independent tour cost in original units (``true_cost * horizon``).
+Host-side list handling stays in numpy / Python like the reference's; the model work runs through the CUDA library
+(no CPU fallback)."""
+import time
+from copy import deepcopy
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .driver import rollout
+from .routing.formats import RPInstance
+
+__all__ = ["read_solomon", "Destructor", "LNS"]
+
+
+def read_solomon(path: str) -> RPInstance:
+    """Solomon / Gehring-Homberger text file -> normalised RPInstance (io_utils.py:24-128): coordinates / 100,
+    demand / capacity, windows and service time / horizon (= depot due date)."""
+    rows, kv, cap = [], None, None
+    with open(path, "rt") as f:
+        for i, line in enumerate(f, start=1):
+            v = line.split()
+            if i == 5:
+                kv, cap = int(v[0]), float(v[1])
+            elif i >= 10 and len(v) == 7:
+                rows.append([float(x) for x in v])
+    a = np.asarray(rows, dtype=np.float64)
+    horizon = a[0, 5]
+    coords = a[:, 1:3] / 100.0
+    demand = a[:, 3] / cap
+    tw = a[:, 4:6] / horizon
+    service = a[:, 6] / horizon
+    assert np.all(service[1:] == service[1])
+    has_tw = a[1:, 4] != 0
+    return RPInstance(coords=coords, demands=demand, tw=tw, service_time=service[1], graph_size=coords.shape[0],
+                      org_service_horizon=horizon, max_vehicle_number=kv, vehicle_capacity=1.0, service_horizon=1.0,
+                      depot_idx=[0], type="1" if cap < 500 else "2", tw_frac=str(has_tw.sum() / has_tw.size))
+
+
+class Destructor:
+    """Restatement of ``lib/lns/destructor.py`` (random_from_route family).  Solutions are lists of tours; complete
+    tours are emitted as ``[0, ..., 0]``, destroyed ones as open customer lists (the convention import_sol reads,
+    env.py:578-581)."""
+    RM_P_MODES = ("random_nodes", "random_cut", "const_cut")
+
+    def __init__(self, num_partial: int, rm_partial_mode: str = "random", rm_complete_mode: str = "random",
+                 frac_rm_nodes_from_partial: float = 0.5, frac_rm_complete_routes: float = 0.15, seed: int = 1):
+        assert rm_partial_mode in self.RM_P_MODES + ("random",)
+        assert rm_complete_mode in ("random", "smallest")
+        assert 0 <= frac_rm_nodes_from_partial < 1 and 0 <= frac_rm_complete_routes < 1
+        self.num_partial = num_partial
+        self.rm_partial_mode = rm_partial_mode
+        self.rm_complete_mode = rm_complete_mode
+        self.frac_p = frac_rm_nodes_from_partial
+        self.frac_c = frac_rm_complete_routes
+        self.rnd = np.random.default_rng(seed)
+
+    def _rnd_int_1(self, n: int) -> int:          # destructor.py:58-63: 1 <= x < n-1, or 1
+        return 1 if n <= 2 else int(self.rnd.integers(1, n - 1))
+
+    def _partial(self, tour: List[int]) -> List[int]:
+        if tour[0] == 0 and tour[-1] == 0:
+            tour = tour[1:-1]
+        mode = self.rm_partial_mode
+        if mode == "random":
+            mode = str(self.rnd.choice(self.RM_P_MODES))
+        n = len(tour)
+        if mode == "random_nodes":               # destructor.py:141-149
+            n_rm = int(max(round(self.frac_p * n), 1)) if self.frac_p > 0 else self._rnd_int_1(n)
+            rm = set(self.rnd.choice(np.arange(n), size=min(n_rm, n), replace=False).tolist())
+            return [e for i, e in enumerate(tour) if i not in rm]
+        if mode == "random_cut":                 # :151-155
+            return tour[: self._rnd_int_1(n)]
+        assert self.frac_p > 0                   # const_cut :157-161
+        return tour[: -int(max(round(self.frac_p * n), 1))]
+
+    def _rm_complete(self, tours: List[List[int]]) -> List[List[int]]:
+        if self.frac_c <= 0 or not tours:
+            return tours
+        n_c = len(tours)
+        n_rm = int(max(round(self.frac_c * n_c), 1))
+        if self.rm_complete_mode == "random":
+            rm = set(self.rnd.choice(np.arange(n_c), size=n_rm, replace=False).tolist())
+        else:
+            rm = set(np.argsort(np.array([len(t) for t in tours]))[:n_rm].tolist())
+        return [t for i, t in enumerate(tours) if i not in rm]
+
+    def random_from_route(self, sol: List[List[int]]) -> List[List[int]]:     # destructor.py:86-121
+        lens = np.array([len(t) for t in sol])
+        closed = sol[0][0] == 0 and sol[0][-1] == 0
+        max_idx = 3 if closed else 1
+        cand = np.flatnonzero(lens > max_idx)
+        pick = set(self.rnd.choice(cand, min(self.num_partial, cand.size), replace=False).tolist()) if cand.size else set()
+        c_tours, p_tours = [], []
+        for i, tour in enumerate(sol):
+            if i in pick:
+                p_tours.append(self._partial(list(tour)))
+            elif len(tour) > max_idx:
+                c_tours.append(list(tour) if closed else [0] + list(tour) + [0])
+        return self._rm_complete(c_tours) + p_tours
+
+    def destruct(self, solutions: Sequence[List[List[int]]]) -> List[List[List[int]]]:
+        return [self.random_from_route(s) for s in solutions]
+
+
+class LNS:
+    """``LNS(instance, policy, ...).search(time_limit=..)`` — the reference's loop without local search."""
+
+    def __init__(self, instance: RPInstance, policy, env, num_best: int = 2, num_other: int = 3,
+                 add_best: bool = True, destructor: Optional[Destructor] = None, seed: int = 1234,
+                 use_graph: bool = True):
+        assert env.inference and env.pomo, "LNS construction uses POMO inference (search/default.yaml: pomo_inference)"
+        P = env.num_samples
+        assert P % (num_best + num_other) == 0, "num_samples must be a multiple of num_best + num_other (lns.py:307)"
+        self.inst, self.policy, self.env = instance, policy, env
+        self.num_best, self.num_other, self.add_best = num_best, num_other, add_best
+        self.ds = destructor or Destructor(num_partial=env.max_concurrent_vehicles, seed=seed)
+        self.use_graph = use_graph
+        self.horizon = float(instance.org_service_horizon)
+        self.best_solution, self.best_cost, self.best_true_cost, self.best_step = None, float("inf"), float("inf"), -1
+        self.step = 0
+        self.history: List[Tuple[float, float, float]] = []      # (seconds, incumbent env cost, incumbent true cost)
+        env.seed(seed)
+
+    # ------------------------------------------------------------------ one construction / repair (lns.py:236-275)
+    @torch.no_grad()
+    def _construct(self, partial: Optional[List[List[List[int]]]] = None):
+        env, pol = self.env, self.policy
+        if partial is None:
+            pol.set_decode_type("greedy")
+            pol.reset_static()
+            env.load_data([self.inst])
+            env.reset()
+        else:
+            env.import_sol([partial])
+        rollout(pol, env, graph=self.use_graph and partial is None)
+        true = env.true_cost() * self.horizon
+        sols, costs = env.export_sol(self.num_best, self.num_other, mode="random")
+        # recover which samples were exported to attach their batch-independent cost
+        total = env.state["total"].cpu().numpy()
+        tc = true.cpu().numpy()
+        out_true = []
+        for c in costs[0]:
+            j = int(np.flatnonzero(total == np.float32(c))[0])
+            out_true.append(float(tc[j]))
+        return sols[0], (np.asarray(costs[0]) * self.horizon).tolist(), out_true
+
+    def _select_best(self, sols, costs, true_costs):
+        j = int(np.argmin(costs))
+        if self.best_solution is None or costs[j] < self.best_cost:
+            self.best_solution, self.best_cost, self.best_true_cost = deepcopy(sols[j]), costs[j], true_costs[j]
+            self.best_step = self.step
+
+    def _add_best(self, sols, costs, true_costs):                 # lns.py:209-222
+        if self.best_cost not in costs:
+            w = int(np.argmax(costs))
+            sols[w], costs[w], true_costs[w] = deepcopy(self.best_solution), self.best_cost, self.best_true_cost
+        return sols, costs, true_costs
+
+    def search(self, time_limit: Optional[float] = None, num_steps: Optional[int] = None):
+        assert time_limit is not None or num_steps is not None
+        t0 = time.time()
+        P = self.env.num_samples
+        sols, costs, tcs = self._construct()
+        self._select_best(sols, costs, tcs)
+        self.history.append((time.time() - t0, self.best_cost, self.best_true_cost))
+        slowest = 0.0
+        while True:
+            if num_steps is not None and self.step >= num_steps:
+                break
+            if time_limit is not None and (time.time() - t0) >= max(time_limit - slowest, 0.0):
+                break
+            ts = time.time()
+            if self.add_best:
+                sols, costs, tcs = self._add_best(sols, costs, tcs)
+            boot = [deepcopy(s) for s in sols] * (P // len(sols))              # lns.py:304-310
+            partial = self.ds.destruct(boot)
+            self.step += 1
+            sols, costs, tcs = self._construct(partial)
+            self._select_best(sols, costs, tcs)
+            slowest = max(slowest, time.time() - ts)
+            self.history.append((time.time() - t0, self.best_cost, self.best_true_cost))
+        return self.best_solution, self.best_cost, self.best_true_cost

@@ -220,13 +220,21 @@ class RPEnv:
         the window fix-up (env.py:395-409) modifies ``tw`` in place.  ``check=False`` skips the one
         device->host read that turns a collapsed window into the reference's AssertionError."""
         dev = self.device
-        up = lambda t: t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous().clone() \
-            if t.device == dev else t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-        self.coords = up(arrays["coords"])
-        self.demands = up(arrays["demands"])
-        self.tw = up(arrays["tw"])
-        self.service_time = up(arrays["service_time"])
-        self.org_service_horizon = up(arrays["org_service_horizon"])
+
+        def up(name, t):
+            # persistent device buffers: the same pointers across loads of equally shaped batches (lets callers
+            # replay a captured CUDA graph of the rollout); always a copy, never an alias of the caller's tensor
+            cur = getattr(self, name)
+            if cur is None or tuple(cur.shape) != tuple(t.shape):
+                cur = torch.empty(tuple(t.shape), dtype=torch.float32, device=dev)
+                setattr(self, name, cur)
+            cur.copy_(t.to(dtype=torch.float32) if t.device != dev else t.to(torch.float32), non_blocking=True)
+
+        up("coords", arrays["coords"])
+        up("demands", arrays["demands"])
+        up("tw", arrays["tw"])
+        up("service_time", arrays["service_time"])
+        up("org_service_horizon", arrays["org_service_horizon"])
         I, gs = int(self.coords.size(0)), int(self.coords.size(1))
         kv = int(max_vehicle_number)
         self.n_inst = I
