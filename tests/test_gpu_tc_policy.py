@@ -137,3 +137,44 @@ def test_tc_sampling_uses_given_uniforms():
             obs, _, done, _ = env.step(action)
             if done:
                 break
+
+
+@pytest.mark.parametrize("n_customers,k_frac,K,P", [(119, 0.25, 3, 4), (127, 0.1, 4, 2), (60, 0.4, 1, 4), (12, 0.5, 2, 4)])
+def test_tc_matches_fp32_path_other_shapes(n_customers, k_frac, K, P):
+    """Shapes outside the golden fixtures (graph sizes up to the 128-row tile, 1..4 concurrent vehicles; N > 104 runs
+    the one-CTA-per-SM tiling, the others the two-CTA tiling): the tensor-core step against the fp32 CUDA path,
+    teacher-forced with the fp32 path's greedy actions."""
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.synth import sample_instances
+    from jampr_plus_b200.weights import random_state_dict
+    inst = sample_instances(3, graph_size=n_customers, seed=5)
+    envs, pols = [], []
+    for prec in ("fp32", "fp16"):
+        env = RPEnv(max_concurrent_vehicles=K, k_nbh_frac=k_frac, pomo=True, pomo_nbh_frac=0.6, num_samples=P,
+                    inference=True, device="cuda")
+        env.seed(3)
+        pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=prec)
+        pol.load_state_dict(random_state_dict(1))
+        pol.return_logp = True
+        env.load_data(inst)
+        envs.append(env)
+        pols.append(pol)
+    obs0 = envs[0].reset()
+    obs1 = envs[1].reset(start_nodes=envs[0]._start_nodes)
+    worst, done, steps = 0.0, False, 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        while not done:
+            assert torch.equal(obs0.nbh, obs1.nbh) and torch.equal(obs0.nbh_mask, obs1.nbh_mask)
+            action, _, _ = pols[0](obs0)
+            pols[1](obs1)
+            l0, l1 = pols[0].log_probs(envs[0]), pols[1].log_probs(envs[1])
+            fin = torch.isfinite(l0)
+            assert torch.equal(fin, torch.isfinite(l1))
+            worst = max(worst, float((l0[fin] - l1[fin]).abs().max()))
+            obs0, c0, done, _ = envs[0].step(action)
+            obs1, c1, _, _ = envs[1].step(action)
+            assert torch.equal(c0, c1)
+            steps += 1
+    assert worst <= LOGP_ATOL["fp16"], worst
+    assert steps > n_customers // 2
