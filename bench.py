@@ -284,6 +284,7 @@ def main():
 
     # ---- instrumented episode: CUDA events around every launch of the dominant kernel (tour-graph GNN)
     roof = None
+    env_roof = None
     if rank == 0:
         env.load_arrays(resident, kv, check=False)
         pol.reset_static()
@@ -292,7 +293,7 @@ def main():
         st.ensure_policy_buffers(False)
         w = pol.encode_static(env)
         lib, d, p, S = pol._lib, env._dims, env._inst, env._stream()
-        evs = []
+        evs, env_evs = [], []
         cap = env.graph_size + env.max_vehicle_number + 1
         step = env._step
         fused = args.precision != "fp32"      # tensor-core path: GNN + decoder are ONE kernel per step
@@ -307,7 +308,10 @@ def main():
             evs.append((a, b))
             if not fused:
                 _cabi.check(lib.jampr_policy_step(d, p, w, st.struct(), 0, step, 0, 0, None, S), "jampr_policy_step")
+            c = torch.cuda.Event(enable_timing=True)
             _cabi.check(lib.jampr_env_step(d, p, st.struct(), None, step, S), "jampr_env_step")
+            c.record()
+            env_evs.append((b, c) if fused else None)
             step += 1
         torch.cuda.synchronize()
         done2 = int(st["ctl"][_cabi.CTL_DONE_STEP].item())
@@ -321,9 +325,26 @@ def main():
             peaks = json.load(open(pk_path))
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = fl / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "policy_step_tc (tour-graph GNN + decoder, fused)" if fused else "tour_encoder_f32",
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "traffic_policy_step.json")
+        if fused and args.precision == "fp16" and I == 4096 and os.path.exists(tr_path):
+            tr = json.load(open(tr_path))      # one ncu --set full capture of this very launch shape (see `source`)
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        if fused:
+            # the environment step (env_move + env_observe): HBM-bound integer / compare work, SURVEY.md §8d figure of
+            # ~1.5 KB per rollout and step (candidate rows, state read + write, observation)
+            live_env = [x[0].elapsed_time(x[1]) for i, x in enumerate(env_evs) if x is not None and env._step + i <= done2]
+            env_ms = float(np.mean(live_env))
+            A_env = ENV_KW["max_concurrent_vehicles"] * env.k_nbh_size
+            env_bytes = (A_env * 14 + 16 + 140 + 3 * A_env) * bs
+            hbm = float(peaks.get("hbm_gbs", 6650.0))
+            env_roof = {"bound": "hbm", "kernel": "env_move + env_observe", "achieved": env_bytes / (env_ms * 1e-3) / 1e9,
+                        "peak": hbm, "unit": "GB/s", "frac": env_bytes / (env_ms * 1e-3) / 1e9 / hbm,
+                        "bytes_per_launch_pair": env_bytes, "avg_ms": env_ms,
+                        "share_of_step": env_ms * len(live_env) / (ms_res / args.steps)}
+        roof = {"bound": "tensor", "kernel": "policy_step_tc2 (tour-graph GNN + decoder, fused)" if fused else "tour_encoder_f32",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None,
+                "frac": ach / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                 "flops_per_launch": fl, "avg_launch_ms": avg_ms, "launches_timed": len(live),
                 "share_of_step": avg_ms * len(live) / (ms_res / args.steps)}
@@ -355,6 +376,8 @@ def main():
         "clocks": clk,
         "roofline": roof,
     }
+    if env_roof is not None:
+        res["roofline_env"] = env_roof
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         r, t, c = cpu_port_rollouts(inst[: args.cpu_sample], threads)
