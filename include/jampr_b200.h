@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define JAMPR_ABI_VERSION 2
+#define JAMPR_ABI_VERSION 3
 
 /* argument errors */
 #define JAMPR_E_BADARG   (-1)
@@ -84,6 +84,9 @@ typedef struct {
                               (source-row offset | 16-bit weight, csrc/policy_tc_common.cuh agg_entry), written by
                               jampr_node_encoder for the precision in use; may be NULL on the fp32 path */
   uint32_t*    tc_dtab;    /* out (I,nd) nd = N rounded up to 8: packed edges node -> depot, same encoding */
+  void*        lg_h16;     /* scratch (2,I,Npad,128) 16-bit, Npad = N rounded up to 128: node-encoder ping-pong embedding of
+                              the large-graph path (N > 128, csrc/gnn_large.cu); NULL otherwise */
+  float*       lg_skip;    /* scratch (I,Npad,128) fp32 skip operand of the same path; NULL otherwise */
   const float* dist_given; /* in  (I,N,N) or NULL: caller-supplied normalised transit matrix copied into `dist`
                               instead of evaluating the DIMACS formula (e.g. a matrix computed by torch on the
                               host: MKL's vsSqrt is not correctly rounded, sqrtf on the device is) */
@@ -118,6 +121,9 @@ typedef struct {
   float*    ne;        /* (bs,N,256)    node_emb = node_emb_output_proj(h) + static_emb (tour_encoder.py:217-218) */
   float*    ne_stats;  /* (bs,2,256)    column mean and max of ne over the N nodes (policy.py:179-181) */
   int32_t*  ctl;       /* (JAMPR_CTL_WORDS) control block */
+  void*     hbuf;      /* (2,bs,Npad,128) 16-bit ping-pong tour-graph embedding of the large-graph path (N > 128), or NULL */
+  float*    hskip;     /* (bs,Npad,128) fp32 skip operand of the large-graph path, or NULL */
+  float*    stats_part;/* (bs,Npad/128,2,256) per-tile column sums / maxima of ne (large-graph path), or NULL */
 } jampr_state_t;
 
 /* Policy weights: one fp32 blob on the device, packed by jampr_plus_b200/model/packing.py.

@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libjampr_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 ST_NO_FEASIBLE, ST_TOUR_OVERFLOW, ST_FLEET_EXHAUSTED, ST_NAN_LOGITS, ST_TW_COLLAPSE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLING = 0, 1
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
@@ -28,12 +28,12 @@ class Dims(C.Structure):
 class Instances(C.Structure):
     _fields_ = [(n, _p) for n in
                 ("coords", "demand", "tw", "service", "horizon", "dist", "ttd", "knn", "knn_w", "order",
-                 "inst_status", "static_emb", "h0", "tc_tab", "tc_dtab", "dist_given")]
+                 "inst_status", "static_emb", "h0", "tc_tab", "tc_dtab", "lg_h16", "lg_skip", "dist_given")]
 
 
 STATE_FIELDS = ("visited", "pred", "succ", "plan", "vflags", "row", "nxt", "cur", "row_last", "cap", "time", "cttd",
                 "total", "cost", "status", "allvis", "nvis", "nbh", "mask", "action", "ll", "entropy", "logp",
-                "h_fin", "ne", "ne_stats", "ctl")
+                "h_fin", "ne", "ne_stats", "ctl", "hbuf", "hskip", "stats_part")
 
 
 class State(C.Structure):

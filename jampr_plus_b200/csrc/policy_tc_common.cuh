@@ -13,7 +13,8 @@ using namespace tc;
 #define W16_GK (W16_CTXT + 512 * 256)                   // [256][256]  set_proj rows 0..255 as stored
 #define W16_GV (W16_GK + 256 * 256)                     // [256][256]  set_proj rows 256..511, transposed
 #define W16_M1 (W16_GV + 256 * 256)                     // [256][256]  (W_lk^T W_out)^T
-#define W16_END (W16_M1 + 256 * 256)
+#define W16_NE (W16_M1 + 256 * 256)                     // 20 stages: node-encoder layers 0..2, output_proj halves, TE input proj
+#define W16_END (W16_NE + 20 * W16_STAGE)
 
 struct PtArgs {
   jampr_dims_t d;

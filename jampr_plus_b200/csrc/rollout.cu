@@ -16,6 +16,10 @@ int jampr_policy_step_tc2(const jampr_dims_t*, const jampr_instances_t*, const j
                           int, int, int, uint64_t, const float*, int, cudaStream_t);
 int64_t jampr_w16_elems(void);
 int jampr_tc_prepare(const jampr_dims_t*, const jampr_instances_t*, int, cudaStream_t);
+int jampr_lg_node_encoder(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, cudaStream_t);
+int jampr_lg_tour_encoder(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, const jampr_state_t*,
+                          int, cudaStream_t);
+#define JAMPR_TILE_NODES 128     // graphs up to this size run the single-tile kernels, larger ones the layer-wise path
 
 // Tensor-core policy step: the two-CTAs-per-SM tiling (policy_tc2.cu) when the graph fits it, else the one-CTA
 // tiling (policy_tc.cu).  JAMPR_TC_VARIANT=1 forces the latter (A/B measurements).
@@ -64,6 +68,8 @@ extern "C" int jampr_node_encoder(const jampr_dims_t* d, const jampr_instances_t
   if (rc) return rc;
   // once per episode and < 1 % of it: every precision runs the fp32 kernel, the tensor-core step kernel
   // converts h0 / static_emb on the fly
+  if (w->precision != JAMPR_PREC_F32 && d->n_nodes > JAMPR_TILE_NODES)
+    return jampr_lg_node_encoder(d, inst, w, (cudaStream_t)stream);
   if (w->precision != JAMPR_PREC_F32) {
     const int rc2 = jampr_tc_prepare(d, inst, w->precision, (cudaStream_t)stream);
     if (rc2) return rc2;
@@ -79,6 +85,8 @@ extern "C" int jampr_tour_encoder(const jampr_dims_t* d, const jampr_instances_t
   cudaStream_t s = (cudaStream_t)stream;
   // on the tensor-core path the encoder is fused with the decoder: the call runs the whole policy step (greedy)
   // and additionally stores h_fin / ne / ne_stats
+  if (w->precision != JAMPR_PREC_F32 && d->n_nodes > JAMPR_TILE_NODES)
+    return jampr_lg_tour_encoder(d, inst, w, st, step_no, s);
   if (w->precision != JAMPR_PREC_F32)
     return policy_step_tc_any(d, inst, w, st, 1, step_no, JAMPR_DECODE_GREEDY, 0, nullptr, 1, s);
   return jampr_tour_encoder_f32(d, inst, st, w->blob, step_no, s);
@@ -92,6 +100,14 @@ extern "C" int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t*
   if (!st || (decode_type != JAMPR_DECODE_GREEDY && decode_type != JAMPR_DECODE_SAMPLING)) return JAMPR_E_BADARG;
   if (!st->h_fin || !st->ne || !st->ne_stats) return JAMPR_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (w->precision != JAMPR_PREC_F32 && d->n_nodes > JAMPR_TILE_NODES) {
+    // large-graph path: layer-wise tensor-core GNN through HBM/L2, then the fp32 decoder kernel
+    if (graph_fresh) {
+      rc = jampr_lg_tour_encoder(d, inst, w, st, step_no, s);
+      if (rc) return rc;
+    }
+    return jampr_decoder_launch(d, inst, st, w->blob, step_no, decode_type, seed, uniforms, s);
+  }
   if (w->precision != JAMPR_PREC_F32)
     return policy_step_tc_any(d, inst, w, st, graph_fresh, step_no, decode_type, seed, uniforms,
                               (d->upd_step != 1) || st->logp != nullptr, s);

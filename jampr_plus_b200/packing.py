@@ -104,7 +104,9 @@ def pack_tc(sd: Dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16) ->
       lin_root.weight], dim=1) (128 x 256; K-blocks 0,1 multiply the aggregated messages, 2,3 the node itself);
       then node_emb_output_proj.weight as two 128-row halves x two K-blocks;
     * decoder mat-vec matrices stored [K][256] (input-major): per-tour-mean half of tour output_proj, ctxt_proj^T,
-      set_proj[0:256] as stored, set_proj[256:512]^T, and M1^T = out_proj^T @ set_proj[512:768] (computed in fp64)."""
+      set_proj[0:256] as stored, set_proj[256:512]^T, and M1^T = out_proj^T @ set_proj[512:768] (computed in fp64);
+    * 20 more weight stages for the large-graph path: the node-encoder blocks, its output_proj and the hoisted
+      node_emb_input_proj."""
     assert dtype in (torch.bfloat16, torch.float16)
     sd = {k: v.detach().to(torch.float32).cpu() for k, v in validate_state_dict(sd).items()}
     parts = []
@@ -120,6 +122,16 @@ def pack_tc(sd: Dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16) ->
     for m in (sd["tour_encoder.output_proj.weight"][:, 128:].t(), sd["decoder.ctxt_proj.weight"].t(), sp[0:256],
               sp[256:512].t(), m1t):
         parts.append(m.contiguous().to(dtype).reshape(-1))
+    # large-graph path (csrc/gnn_large.cu): node-encoder GraphConv blocks, node_encoder.output_proj (two 128-row
+    # halves) and tour_encoder.node_emb_input_proj (128 x 256) as 4 + 4 + 4 + 4 + 4 more weight stages
+    for i in range(3):
+        prefix = f"node_encoder.layers.{i}"
+        wcat = torch.cat((sd[f"{prefix}.conv.lin_rel.weight"], sd[f"{prefix}.conv.lin_root.weight"]), 1)
+        parts.append(sw128_image(wcat.to(dtype)))
+    wno = sd["node_encoder.output_proj.weight"]
+    for half in range(2):
+        parts.append(sw128_image(wno[half * 128:(half + 1) * 128].contiguous().to(dtype)))
+    parts.append(sw128_image(sd["tour_encoder.node_emb_input_proj.weight"].contiguous().to(dtype)))
     blob = torch.cat(parts)
     lib = _cabi.load_library()
     assert blob.numel() == lib.jampr_weight_blob16_elems(), (blob.numel(), lib.jampr_weight_blob16_elems())

@@ -58,6 +58,12 @@ _POLICY_SPEC = {
     "ne": (torch.float32, lambda s: (s.bs, s.N, 256)),
     "ne_stats": (torch.float32, lambda s: (s.bs, 2, 256)),
 }
+# large-graph path only (N > 128: the graph spans several 128-row tiles, csrc/gnn_large.cu)
+_LARGE_SPEC = {
+    "hbuf": (torch.int16, lambda s: (2, s.bs, (s.N + 127) // 128 * 128, 128)),
+    "hskip": (torch.float32, lambda s: (s.bs, (s.N + 127) // 128 * 128, 128)),
+    "stats_part": (torch.float32, lambda s: (s.bs, (s.N + 127) // 128, 2, 256)),
+}
 
 
 class DeviceState:
@@ -80,6 +86,11 @@ class DeviceState:
             if name not in self.t:
                 self.t[name] = torch.zeros(shp(self), dtype=dt, device=self.device)
                 changed = True
+        if self.N > 128:
+            for name, (dt, shp) in _LARGE_SPEC.items():
+                if name not in self.t:
+                    self.t[name] = torch.zeros(shp(self), dtype=dt, device=self.device)
+                    changed = True
         self.want_logp = self.want_logp or want_logp
         if changed:
             self._struct = None
@@ -179,6 +190,7 @@ class RPEnv:
         self._knn = self._knn_w = None
         self._static_emb = self._h0 = None
         self._tc_tab = self._tc_dtab = None
+        self._lg_h16 = self._lg_skip = None
         self._inst_status = None
         self._dims = None
         self._inst = None
@@ -260,6 +272,11 @@ class RPEnv:
             # packed edge tables of the tensor-core policy step (filled by jampr_node_encoder)
             self._tc_tab = torch.zeros(I, N, (k + 3) // 4 * 4, dtype=torch.int32, device=dev)
             self._tc_dtab = torch.zeros(I, (N + 7) // 8 * 8, dtype=torch.int32, device=dev)
+            self._lg_h16 = self._lg_skip = None
+            if N > 128:      # several 128-row tiles per graph: node-encoder scratch of the large-graph path
+                npad = (N + 127) // 128 * 128
+                self._lg_h16 = torch.zeros(2, I, npad, 128, dtype=torch.int16, device=dev)
+                self._lg_skip = torch.zeros(I, npad, 128, dtype=torch.float32, device=dev)
             self._table_key = shape_key
         self.bs = I * self._num_samples
         self._dims = _cabi.Dims(I, self._num_samples, N, K, k, self.max_vehicle_number, min(64, N),
@@ -270,7 +287,7 @@ class RPEnv:
                         ("dist", self._dist_mat), ("ttd", self.time_to_depot), ("knn", self._knn),
                         ("knn_w", self._knn_w), ("order", self.ordered_idx), ("inst_status", self._inst_status),
                         ("static_emb", self._static_emb), ("h0", self._h0), ("tc_tab", self._tc_tab),
-                        ("tc_dtab", self._tc_dtab)):
+                        ("tc_dtab", self._tc_dtab), ("lg_h16", self._lg_h16), ("lg_skip", self._lg_skip)):
             setattr(p, name, _cabi.ptr(t))
         given = None
         if dist_mat is not None:
