@@ -34,6 +34,8 @@ struct LgArgs {
   int step_no;
   int mode;              // lg_proj: 0 node_emb (+ static_emb, stats), 1 static_emb
   int bias_off;          // lg_proj / lg_h0: fp32 blob offset of the output bias
+  int tab_shift;         // kNN edge entries: source row = (entry & 0xffff) >> tab_shift (7: the single-tile encoding of
+                         // policy_tc_common.cuh agg_entry, shared with the step kernel; 0: plain row index, N > 128)
 };
 
 template <typename T>
@@ -160,10 +162,10 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_layer_kernel(const LgArgs a)
       const uint4* et = reinterpret_cast<const uint4*>(p.tc_tab + (iN + u) * k4);
       for (int j4 = 0; j4 < k4 / 4; ++j4) {
         const uint4 q = __ldg(et + j4);
-        lg_edge<T>(hs, q.x & 0xffffu, from_u32<T2>(__byte_perm(q.x, q.x, 0x3232)), foff, m, j4 == 0);
-        lg_edge<T>(hs, q.y & 0xffffu, from_u32<T2>(__byte_perm(q.y, q.y, 0x3232)), foff, m, false);
-        lg_edge<T>(hs, q.z & 0xffffu, from_u32<T2>(__byte_perm(q.z, q.z, 0x3232)), foff, m, false);
-        lg_edge<T>(hs, q.w & 0xffffu, from_u32<T2>(__byte_perm(q.w, q.w, 0x3232)), foff, m, false);
+        lg_edge<T>(hs, (q.x & 0xffffu) >> a.tab_shift, from_u32<T2>(__byte_perm(q.x, q.x, 0x3232)), foff, m, j4 == 0);
+        lg_edge<T>(hs, (q.y & 0xffffu) >> a.tab_shift, from_u32<T2>(__byte_perm(q.y, q.y, 0x3232)), foff, m, false);
+        lg_edge<T>(hs, (q.z & 0xffffu) >> a.tab_shift, from_u32<T2>(__byte_perm(q.z, q.z, 0x3232)), foff, m, false);
+        lg_edge<T>(hs, (q.w & 0xffffu) >> a.tab_shift, from_u32<T2>(__byte_perm(q.w, q.w, 0x3232)), foff, m, false);
       }
     } else {
       if (st.visited[gN + u]) {
@@ -608,10 +610,11 @@ static int lg_node_encoder_t(const jampr_dims_t* d, const jampr_instances_t* ins
   CUDA_RET(cudaFuncSetAttribute(lg_layer_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_LAYER_SMEM));
   CUDA_RET(cudaFuncSetAttribute(lg_proj_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_PROJ_SMEM));
   CUDA_RET(cudaFuncSetAttribute(lg_h0_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_H0_SMEM));
-  lg_prepare_kernel<T><<<I, 256, 0, s>>>(*d, *inst);
+  if (N > 128) lg_prepare_kernel<T><<<I, 256, 0, s>>>(*d, *inst);     // else: the step kernel's table (jampr_tc_prepare)
   lg_input_kernel<T><<<dim3((N + 1) / 2, I), 256, 0, s>>>(*d, *inst, w->blob, buf0, inst->lg_skip, npad);
   LgArgs a;
   a.d = *d; a.p = *inst; a.st = jampr_state_t{}; a.w = w->blob; a.w16 = w->blob_bf16;
+  a.tab_shift = N > 128 ? 0 : 7;
   a.hskip = inst->lg_skip; a.hfin = nullptr; a.kind = 0; a.per_instance = 1; a.step_no = 0; a.mode = 1; a.bias_off = OFF_NE_OUT_B;
   T* src = buf0;
   T* dst = buf1;
@@ -638,6 +641,7 @@ static int lg_tour_encoder_t(const jampr_dims_t* d, const jampr_instances_t* ins
   lg_start_kernel<T><<<dim3((N * 32 + 255) / 256, bs), 256, 0, s>>>(*d, *inst, *st, buf0, st->hskip, npad, step_no);
   LgArgs a;
   a.d = *d; a.p = *inst; a.st = *st; a.w = w->blob; a.w16 = w->blob_bf16;
+  a.tab_shift = N > 128 ? 0 : 7;
   a.hskip = st->hskip; a.per_instance = 0; a.step_no = step_no; a.mode = 0; a.bias_off = OFF_TE_OUT_B;
   T* src = buf0;
   T* dst = buf1;

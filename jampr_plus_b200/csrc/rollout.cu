@@ -68,12 +68,18 @@ extern "C" int jampr_node_encoder(const jampr_dims_t* d, const jampr_instances_t
   if (rc) return rc;
   // once per episode and < 1 % of it: every precision runs the fp32 kernel, the tensor-core step kernel
   // converts h0 / static_emb on the fly
-  if (w->precision != JAMPR_PREC_F32 && d->n_nodes > JAMPR_TILE_NODES)
-    return jampr_lg_node_encoder(d, inst, w, (cudaStream_t)stream);
-  if (w->precision != JAMPR_PREC_F32) {
+  // Tensor-core precisions: the node encoder runs as tcgen05 GraphConv tiles too (gnn_large.cu, any graph size;
+  // JAMPR_NODE_ENCODER=fp32 keeps the CUDA-core kernel for single-tile graphs).  Once per episode, < 1 % of it.
+  static const bool ne_fp32 = [] {
+    const char* e = getenv("JAMPR_NODE_ENCODER");
+    return e && e[0] == 'f';
+  }();
+  if (w->precision != JAMPR_PREC_F32 && d->n_nodes <= JAMPR_TILE_NODES) {
     const int rc2 = jampr_tc_prepare(d, inst, w->precision, (cudaStream_t)stream);
     if (rc2) return rc2;
   }
+  if (w->precision != JAMPR_PREC_F32 && (d->n_nodes > JAMPR_TILE_NODES || !ne_fp32))
+    return jampr_lg_node_encoder(d, inst, w, (cudaStream_t)stream);
   return jampr_node_encoder_f32(d, inst, w->blob, (cudaStream_t)stream);
 }
 

@@ -272,11 +272,10 @@ class RPEnv:
             # packed edge tables of the tensor-core policy step (filled by jampr_node_encoder)
             self._tc_tab = torch.zeros(I, N, (k + 3) // 4 * 4, dtype=torch.int32, device=dev)
             self._tc_dtab = torch.zeros(I, (N + 7) // 8 * 8, dtype=torch.int32, device=dev)
-            self._lg_h16 = self._lg_skip = None
-            if N > 128:      # several 128-row tiles per graph: node-encoder scratch of the large-graph path
-                npad = (N + 127) // 128 * 128
-                self._lg_h16 = torch.zeros(2, I, npad, 128, dtype=torch.int16, device=dev)
-                self._lg_skip = torch.zeros(I, npad, 128, dtype=torch.float32, device=dev)
+            # scratch of the tensor-core node encoder (csrc/gnn_large.cu): 16-bit ping-pong embedding + fp32 skip
+            npad = (N + 127) // 128 * 128
+            self._lg_h16 = torch.zeros(2, I, npad, 128, dtype=torch.int16, device=dev)
+            self._lg_skip = torch.zeros(I, npad, 128, dtype=torch.float32, device=dev)
             self._table_key = shape_key
         self.bs = I * self._num_samples
         self._dims = _cabi.Dims(I, self._num_samples, N, K, k, self.max_vehicle_number, min(64, N),
