@@ -8,8 +8,8 @@ construction (``_construct``, :236-275) on ``RPEnv`` / ``Policy`` / the fused de
 random / smallest complete-route removal), ``RPEnv.import_sol`` and the repair rollout.
 
 NOT here: the OR-tools guided local search (``lib/lns/gort.py``; OR-tools is neither installed nor pinned by the
-reference), the ``similarity`` / ``waiting_time`` removal modes (difflib / OR-tools infos) and the DIMACS controller
-protocol.  Costs are reported two ways: the environment's own total (what the reference's loop compares, SURVEY.md
+reference), the ``similarity`` / ``waiting_time`` complete-route removal modes of the destructor (they need the
+local search's infos) and the DIMACS controller protocol.  Costs are reported two ways: the environment's own total (what the reference's loop compares, SURVEY.md
 §0.6 / A.6 explains its quirks) and the batch-independent tour cost in original units (``true_cost * horizon``).
 Host-side list handling stays in numpy / Python like the reference's; the model work runs through the CUDA library
 (no CPU fallback)."""
@@ -121,7 +121,7 @@ class LNS:
 
     def __init__(self, instance: RPInstance, policy, env, num_best: int = 2, num_other: int = 3,
                  add_best: bool = True, destructor: Optional[Destructor] = None, seed: int = 1234,
-                 use_graph: bool = True):
+                 use_graph: bool = True, selection_mode: str = "similarity"):
         assert env.inference and env.pomo, "LNS construction uses POMO inference (search/default.yaml: pomo_inference)"
         P = env.num_samples
         assert P % (num_best + num_other) == 0, "num_samples must be a multiple of num_best + num_other (lns.py:307)"
@@ -129,6 +129,7 @@ class LNS:
         self.num_best, self.num_other, self.add_best = num_best, num_other, add_best
         self.ds = destructor or Destructor(num_partial=env.max_concurrent_vehicles, seed=seed)
         self.use_graph = use_graph
+        self.selection_mode = selection_mode          # config_lns/search/default.yaml: "similarity"
         self.horizon = float(instance.org_service_horizon)
         self.best_solution, self.best_cost, self.best_true_cost, self.best_step = None, float("inf"), float("inf"), -1
         self.step = 0
@@ -148,7 +149,7 @@ class LNS:
             env.import_sol([partial])
         rollout(pol, env, graph=self.use_graph and partial is None)
         true = env.true_cost() * self.horizon
-        sols, costs = env.export_sol(self.num_best, self.num_other, mode="random")
+        sols, costs = env.export_sol(self.num_best, self.num_other, mode=self.selection_mode)
         # recover which samples were exported to attach their batch-independent cost
         total = env.state["total"].cpu().numpy()
         tc = true.cpu().numpy()

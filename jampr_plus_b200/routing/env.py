@@ -507,8 +507,8 @@ class RPEnv:
 
     # ------------------------------------------------------------------ solution I/O (env.py:465-718)
     def export_sol(self, num_best: int = 3, num_other: int = 3, mode: str = "random"):
-        """Export tour plans as nested lists (env.py:465-573).  ``mode='similarity'`` (difflib, host-side
-        string matching, seq_match.py) is outside the accelerated path."""
+        """Export tour plans as nested lists (env.py:465-573); ``mode`` = "random" or "similarity" (host-side
+        difflib matching like the reference, jampr_plus_b200/selection.py)."""
         P = self._num_samples
         st = self.state
         plan = st["plan"].view(-1, P, st.K_max, st.L)
@@ -519,9 +519,19 @@ class RPEnv:
                                f"with num_samples = {P} < {n_smp}!")
             cost_idx = total.sort(dim=-1, stable=True).indices
             idx = cost_idx[:, :num_best]
+            if mode == "similarity":
+                # host-side difflib matching like the reference (env.py:498-545, seq_match.py)
+                from ..selection import select_similarity
+                all_tours = self._sol_to_list(plan)
+                all_costs = total.cpu().tolist()
+                tours, costs = [], []
+                for bst, smps, cst in zip(idx.cpu().tolist(), all_tours, all_costs):
+                    t, c = select_similarity(smps, cst, bst, num_other)
+                    tours.append(t)
+                    costs.append(c)
+                return tours, costs
             if mode != "random":
-                raise NotImplementedError(f"selection mode {mode!r} is host-side string matching in the reference "
-                                          f"(seq_match.py) and not part of the accelerated path")
+                raise ValueError(f"unknown selection mode: {mode}.")
             if num_other > 0:
                 w = torch.ones(plan.size(0), P - num_best, device=self.device)
                 rnd = torch.multinomial(w, num_other, replacement=False, generator=self._gen)

@@ -46,3 +46,16 @@ def test_destructor_invariants():
             # at least one complete tour is removed when any exists (frac_rm_complete_routes > 0, destructor.py:188)
             n_cand = sum(len(t) > 1 for t in sol)
             assert len(closed) <= max(n_cand - min(3, n_cand) - 1, 0)
+
+
+def test_similarity_selection_matches_reference():
+    """export_sol(mode="similarity") selection against vectors produced by the reference's seq_match.py and the
+    selection loop of env.py:498-545 (tests/golden/make_selection_golden.py)."""
+    import json
+    from jampr_plus_b200.selection import select_similarity
+    cases = json.load(open(os.path.join(os.path.dirname(DATA), "golden", "selection_similarity.json")))
+    assert len(cases) == 3
+    for c in cases:
+        tours, costs = select_similarity(c["samples"], c["costs"], c["best_idx"], c["num_other"])
+        assert tours == c["tours"]
+        assert costs == c["sel_costs"]
