@@ -91,3 +91,37 @@ def test_gh1000_shape_rollout_smoke():
         seen = plan[b][plan[b] > 0]
         assert len(seen) == len(set(seen.tolist()))
     assert torch.isfinite(total).all()
+
+
+def test_gehring_homberger_files():
+    """Real 1000-customer files through the reader and the device path: C1_10_1 loads and rolls out (K6 overrides);
+    R1_10_1 raises the reference's own time-window fix-up assertion (env.py:408), like 2 of the 60 N1000 files do in
+    the reference."""
+    import os
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.driver import rollout
+    from jampr_plus_b200.lns import read_solomon
+    from jampr_plus_b200.weights import random_state_dict
+    data = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+    c1 = read_solomon(os.path.join(data, "C1_10_1.TXT"))
+    assert c1.graph_size == 1001 and c1.max_vehicle_number == 250
+    env = RPEnv(max_concurrent_vehicles=3, k_nbh_frac=0.05, pomo=True, num_samples=4, inference=True,
+                tour_graph_update_step=4, device="cuda")
+    env.seed(1)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp16")
+    pol.load_state_dict(random_state_dict(0))
+    env.load_data([c1])
+    assert env.max_vehicle_number == 255 and env.k_nbh_size == 51
+    env.reset()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        total, info = rollout(pol, env)
+    assert 0 <= info["done_step"] <= 1001 + 255 + 1
+    assert torch.isfinite(total).all()
+    plan = env.tour_plan.cpu().numpy()
+    for b in range(env.bs):
+        seen = plan[b][plan[b] > 0]
+        assert len(seen) == len(set(seen.tolist()))
+    r1 = read_solomon(os.path.join(data, "R1_10_1.TXT"))
+    with pytest.raises(AssertionError):
+        env.load_data([r1])
