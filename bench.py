@@ -189,7 +189,7 @@ def main():
         return
     import torch.distributed as dist
     from jampr_plus_b200 import Policy, RPEnv, _cabi
-    from jampr_plus_b200.driver import rollout
+    from jampr_plus_b200.driver import rollout, rollout_sharded
     from jampr_plus_b200.weights import random_state_dict
 
     torch.cuda.set_device(local)
@@ -220,7 +220,10 @@ def main():
         env.load_arrays(arrays, kv, check=False)
         pol.reset_static()
         env.reset()
-        _, _ = rollout(pol, env, check=False)
+        if world > 1:      # union-batch termination semantics across the ranks: one 4-byte all_reduce(MAX) per episode
+            rollout_sharded(pol, env)
+        else:
+            rollout(pol, env, check=False)
         iters["n"] = env.graph_size + env.max_vehicle_number + 1 - ENV_KW["max_concurrent_vehicles"] + 1
         return env.gather_best()
 

@@ -52,6 +52,14 @@ extern "C" {
  * is host-known and travels as a launch argument; only data-dependent words live here. */
 #define JAMPR_CTL_N_ALLVIS    0   /* rollouts whose customers are all visited */
 #define JAMPR_CTL_DONE_STEP   1   /* value of env._step at which the episode terminated (env.py:281), -1 = running */
+/* Sharded runs (one process per GPU): the reference terminates on the UNION batch (env.py:281) and its reported
+ * total_cost depends on that step.  With HOLD set by the caller, a shard that reaches its own
+ * finishing condition records the step in LOCAL_DONE and parks (all later launches are no-ops) instead of
+ * finalising; the caller all-reduces MAX over the ranks, writes FINAL_STEP, calls jampr_env_resume for the parked
+ * step and enqueues the remaining steps; the terminal accounting then happens at FINAL_STEP on every rank. */
+#define JAMPR_CTL_HOLD        2   /* in: 1 = park at the local finishing step */
+#define JAMPR_CTL_LOCAL_DONE  3   /* out: env._step at which this shard alone would have terminated, -1 = not yet */
+#define JAMPR_CTL_FINAL_STEP  4   /* in: finishing step of the union batch, -1 = unknown */
 #define JAMPR_CTL_WORDS       8
 
 typedef struct {
@@ -171,6 +179,11 @@ JAMPR_API int jampr_env_reset(const jampr_dims_t* d, const jampr_instances_t* in
  * before the call.  After termination (ctl[DONE_STEP] >= 0 from an earlier call) it is a no-op. */
 JAMPR_API int jampr_env_step(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_state_t* st,
                    const int32_t* action, int32_t step_no, void* stream);
+
+/* Second half of jampr_env_step (termination test, totals, next observation) for step_no alone: resumes a shard
+ * parked by JAMPR_CTL_HOLD once JAMPR_CTL_FINAL_STEP is known. */
+JAMPR_API int jampr_env_resume(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_state_t* st,
+                     int32_t step_no, void* stream);
 
 /* RPEnv.import_sol tail (env.py:681-706): state arrays were filled by the caller from solution
  * lists (plan, vflags, row, nxt, cur, cap, time, cttd, total); derives visited/pred/succ/row_last

@@ -13,7 +13,7 @@ def __getattr__(name):
     if name in ("Policy", "GNN_ATTN_POLICY_CFG"):
         from .model import policy as _p
         return getattr(_p, name)
-    if name in ("rollout", "eval_episode"):
+    if name in ("rollout", "rollout_sharded", "eval_episode"):
         from . import driver as _r
         return getattr(_r, name)
     raise AttributeError(name)

@@ -14,7 +14,7 @@ ABI_VERSION = 3
 ST_NO_FEASIBLE, ST_TOUR_OVERFLOW, ST_FLEET_EXHAUSTED, ST_NAN_LOGITS, ST_TW_COLLAPSE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLING = 0, 1
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
-CTL_N_ALLVIS, CTL_DONE_STEP, CTL_WORDS = 0, 1, 8
+CTL_N_ALLVIS, CTL_DONE_STEP, CTL_HOLD, CTL_LOCAL_DONE, CTL_FINAL_STEP, CTL_WORDS = 0, 1, 2, 3, 4, 8
 ERRORS = {-1: "bad argument", -2: "graph too large for the on-chip tile of this build", -3: "unsupported"}
 
 _p = C.c_void_p
@@ -46,7 +46,7 @@ class Weights(C.Structure):
 
 
 SYMBOLS = ("jampr_abi_version", "jampr_weight_blob_floats", "jampr_weight_blob16_elems", "jampr_weight_offsets", "jampr_setup_instances",
-           "jampr_node_encoder", "jampr_env_reset", "jampr_env_step", "jampr_env_import_finish",
+           "jampr_node_encoder", "jampr_env_reset", "jampr_env_step", "jampr_env_resume", "jampr_env_import_finish",
            "jampr_tour_encoder", "jampr_policy_step", "jampr_rollout", "jampr_gather_best", "jampr_true_cost",
            "jampr_selftest_umma")
 
@@ -71,6 +71,7 @@ def load_library():
     lib.jampr_env_reset.argtypes = [PD, PI, PS, _p, C.c_int32, _p]
     lib.jampr_env_step.argtypes = [PD, PI, PS, _p, C.c_int32, _p]
     lib.jampr_env_import_finish.argtypes = [PD, PI, PS, _p, _p]
+    lib.jampr_env_resume.argtypes = [PD, PI, PS, C.c_int32, _p]
     lib.jampr_tour_encoder.argtypes = [PD, PI, PW, PS, C.c_int32, _p]
     lib.jampr_policy_step.argtypes = [PD, PI, PW, PS, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _p, _p]
     lib.jampr_rollout.argtypes = [PD, PI, PW, PS, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, _p]

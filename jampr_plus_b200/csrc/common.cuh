@@ -33,6 +33,18 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
+// Is the kernel launched for env._step == step_no still live?  Not after the episode terminated (env.py:281), and
+// not while a sharded run is parked at its local finishing step waiting for the global one (JAMPR_CTL_HOLD).
+__device__ __forceinline__ bool jampr_step_active(const int32_t* ctl, int step_no) {
+  const int done_step = ctl[JAMPR_CTL_DONE_STEP];
+  if (done_step >= 0 && done_step < step_no) return false;
+  if (ctl[JAMPR_CTL_HOLD] != 0 && ctl[JAMPR_CTL_FINAL_STEP] < 0) {
+    const int ld = ctl[JAMPR_CTL_LOCAL_DONE];
+    if (ld >= 0 && ld < step_no) return false;
+  }
+  return true;
+}
+
 // Counter-based uniform in [0,1): splitmix64 of (seed, rollout, step). Restated in
 // oracle/rng.py so that sampling runs can be replayed on the CPU.
 __host__ __device__ __forceinline__ float jampr_uniform(uint64_t seed, uint32_t rollout, uint32_t step) {

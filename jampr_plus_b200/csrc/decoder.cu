@@ -29,8 +29,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decoder_kernel(const DecArgs a
   extern __shared__ __align__(16) float dsm[];
   const jampr_dims_t& d = a.d;
   const jampr_state_t& st = a.st;
-  const int done_step = st.ctl[JAMPR_CTL_DONE_STEP];
-  if (done_step >= 0 && done_step < a.step_no) return;
+  if (!jampr_step_active(st.ctl, a.step_no)) return;
   const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh, A = K * k, L = d.plan_len;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ w = a.w;

@@ -400,8 +400,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1)
 tour_encoder_f32_kernel(jampr_dims_t d, jampr_instances_t p, jampr_state_t st, const float* __restrict__ w,
                         int step_no) {
   extern __shared__ __align__(16) float smem[];
-  const int done_step = st.ctl[JAMPR_CTL_DONE_STEP];
-  if (done_step >= 0 && done_step < step_no) return;
+  if (!jampr_step_active(st.ctl, step_no)) return;
   const int N = d.n_nodes, k = d.k_nbh, b = blockIdx.x, ins = b / d.n_samples;
   const EncSmem s = enc_carve(smem, 16 * TM, N, k);
   for (int e = threadIdx.x; e < 16 * TM * HP; e += ENC_THREADS) { s.hs[e] = 0.0f; s.as[e] = 0.0f; }

@@ -178,8 +178,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_move_kernel(jampr_dims_t d, j
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int bs = d.n_inst * d.n_samples;
   if (b >= bs) return;
-  const int done_step = s.ctl[JAMPR_CTL_DONE_STEP];
-  if (done_step >= 0 && done_step < step_no) return;
+  if (!jampr_step_active(s.ctl, step_no)) return;
   const int ins = b / d.n_samples, K = d.n_slots;
   const int slot = action[2 * b], node = action[2 * b + 1];
   const bool before = s.allvis[b] != 0;
@@ -214,10 +213,22 @@ __global__ void __launch_bounds__(ENV_THREADS) env_observe_kernel(jampr_dims_t d
   const int b = blockIdx.x * ENV_WARPS + warp;
   const int bs = d.n_inst * d.n_samples;
   if (b >= bs) return;
-  const int done_step = s.ctl[JAMPR_CTL_DONE_STEP];
-  if (done_step >= 0 && done_step < step_no) return;
+  if (!jampr_step_active(s.ctl, step_no)) return;
   const int ins = b / d.n_samples, K = d.n_slots, N = d.n_nodes;
-  const bool done = (s.ctl[JAMPR_CTL_N_ALLVIS] == bs) || (step_no >= N + d.k_max + 1);
+  const bool local_done = (s.ctl[JAMPR_CTL_N_ALLVIS] == bs) || (step_no >= N + d.k_max + 1);
+  bool done = local_done;
+  if (s.ctl[JAMPR_CTL_HOLD] != 0) {
+    const int fin = s.ctl[JAMPR_CTL_FINAL_STEP];
+    if (fin < 0) {
+      // sharded run, union finishing step not known yet: park here without finalising or observing
+      if (local_done) {
+        if (b == 0 && lane == 0) s.ctl[JAMPR_CTL_LOCAL_DONE] = step_no;
+        return;
+      }
+    } else {
+      done = step_no >= fin;
+    }
+  }
   if (done) {
     // every vehicle still en route drives home (env.py:1133-1170); unvisited customers become
     // singleton tours at 2 * time_to_depot (env.py:287-295)
@@ -360,6 +371,7 @@ extern "C" int jampr_env_reset(const jampr_dims_t* d, const jampr_instances_t* i
   CUDA_RET(cudaMemsetAsync(st->vflags, 0, bs * d->k_max, s));
   CUDA_RET(cudaMemsetAsync(st->ctl, 0, sizeof(int32_t) * JAMPR_CTL_WORDS, s));
   CUDA_RET(cudaMemsetAsync(st->ctl + JAMPR_CTL_DONE_STEP, 0xff, sizeof(int32_t), s));
+  CUDA_RET(cudaMemsetAsync(st->ctl + JAMPR_CTL_LOCAL_DONE, 0xff, 2 * sizeof(int32_t), s));   // LOCAL_DONE, FINAL_STEP = -1
   const int grid = (int)((bs + ENV_WARPS - 1) / ENV_WARPS);
   env_reset_kernel<<<grid, ENV_THREADS, ENV_WARPS * d->k_nbh * sizeof(int16_t), s>>>(*d, *inst, *st,
                                                                                      start_nodes, n_start);
@@ -378,6 +390,16 @@ extern "C" int jampr_env_step(const jampr_dims_t* d, const jampr_instances_t* in
   return launch_status();
 }
 
+extern "C" int jampr_env_resume(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_state_t* st,
+                                int32_t step_no, void* stream) {
+  if (check_dims(d) || !inst || !st) return JAMPR_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bs = (size_t)d->n_inst * d->n_samples;
+  const int grid = (int)((bs + ENV_WARPS - 1) / ENV_WARPS);
+  env_observe_kernel<<<grid, ENV_THREADS, ENV_WARPS * d->k_nbh * sizeof(int16_t), s>>>(*d, *inst, *st, step_no);
+  return launch_status();
+}
+
 extern "C" int jampr_env_import_finish(const jampr_dims_t* d, const jampr_instances_t* inst,
                                        const jampr_state_t* st, int32_t* max_step_out, void* stream) {
   if (check_dims(d) || !inst || !st || !max_step_out) return JAMPR_E_BADARG;
@@ -388,6 +410,7 @@ extern "C" int jampr_env_import_finish(const jampr_dims_t* d, const jampr_instan
   CUDA_RET(cudaMemsetAsync(st->succ, 0, bs * N * sizeof(int16_t), s));
   CUDA_RET(cudaMemsetAsync(st->ctl, 0, sizeof(int32_t) * JAMPR_CTL_WORDS, s));
   CUDA_RET(cudaMemsetAsync(st->ctl + JAMPR_CTL_DONE_STEP, 0xff, sizeof(int32_t), s));
+  CUDA_RET(cudaMemsetAsync(st->ctl + JAMPR_CTL_LOCAL_DONE, 0xff, 2 * sizeof(int32_t), s));
   CUDA_RET(cudaMemsetAsync(max_step_out, 0, sizeof(int32_t), s));
   const int grid = (int)((bs + ENV_WARPS - 1) / ENV_WARPS);
   env_import_kernel<<<grid, ENV_THREADS, ENV_WARPS * d->k_nbh * sizeof(int16_t), s>>>(*d, *inst, *st, max_step_out);

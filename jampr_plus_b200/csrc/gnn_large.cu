@@ -83,8 +83,7 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_layer_kernel(const LgArgs a)
   const jampr_instances_t& p = a.p;
   const jampr_state_t& st = a.st;
   if (!a.per_instance) {
-    const int done_step = st.ctl[JAMPR_CTL_DONE_STEP];
-    if (done_step >= 0 && done_step < a.step_no) return;
+    if (!jampr_step_active(st.ctl, a.step_no)) return;
   }
   const int N = d.n_nodes, k = d.k_nbh, k4 = (k + 3) & ~3;
   const int tile = blockIdx.x, g = blockIdx.y, npad = gridDim.x * 128;
@@ -330,8 +329,7 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_proj_kernel(const LgArgs a, 
   const jampr_dims_t& d = a.d;
   const jampr_instances_t& p = a.p;
   if (!a.per_instance) {
-    const int done_step = a.st.ctl[JAMPR_CTL_DONE_STEP];
-    if (done_step >= 0 && done_step < a.step_no) return;
+    if (!jampr_step_active(a.st.ctl, a.step_no)) return;
   }
   const int N = d.n_nodes;
   const int tile = blockIdx.x, g = blockIdx.y, npad = gridDim.x * 128;
@@ -441,8 +439,7 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_proj_kernel(const LgArgs a, 
 
 // column mean / max of node_emb over all nodes (policy.py:179-181) from the per-tile partials
 __global__ void lg_stats_kernel(jampr_dims_t d, jampr_state_t st, const float* __restrict__ stats_part, int nt, int step_no) {
-  const int done_step = st.ctl[JAMPR_CTL_DONE_STEP];
-  if (done_step >= 0 && done_step < step_no) return;
+  if (!jampr_step_active(st.ctl, step_no)) return;
   const int g = blockIdx.x, c = threadIdx.x;
   float s = 0.0f, m = -INFINITY;
   for (int t = 0; t < nt; ++t) {
@@ -572,8 +569,7 @@ __global__ void lg_input_kernel(jampr_dims_t d, jampr_instances_t p, const float
 template <typename T>
 __global__ void lg_start_kernel(jampr_dims_t d, jampr_instances_t p, jampr_state_t st, T* __restrict__ h16,
                                 float* __restrict__ hskip, int npad, int step_no) {
-  const int done_step = st.ctl[JAMPR_CTL_DONE_STEP];
-  if (done_step >= 0 && done_step < step_no) return;
+  if (!jampr_step_active(st.ctl, step_no)) return;
   const int N = d.n_nodes, g = blockIdx.y, ins = g / d.n_samples;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;       // float4 index inside the graph
   if (e >= N * 32) return;

@@ -211,8 +211,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   const jampr_dims_t& d = a.d;
   const jampr_state_t& st = a.st;
   const jampr_instances_t& p = a.p;
-  const int done_step = st.ctl[JAMPR_CTL_DONE_STEP];
-  if (done_step >= 0 && done_step < a.step_no) return;
+  if (!jampr_step_active(st.ctl, a.step_no)) return;
   const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh, A = K * k, L = d.plan_len;
   const int k4 = (k + 3) & ~3, nd = (N + 7) & ~7;
   const int b = blockIdx.x, ins = b / d.n_samples;

@@ -11,7 +11,7 @@ import torch
 from . import _cabi
 from .routing.formats import RPInstance
 
-__all__ = ["rollout", "eval_episode"]
+__all__ = ["rollout", "rollout_sharded", "eval_episode"]
 
 
 _GRAPHS: Dict = {}
@@ -73,6 +73,45 @@ def rollout(policy, env, max_steps: Optional[int] = None, check: bool = True,
             env._step += rc
         info = {"done_step": done_step, "steps_enqueued": rc}
     return st["total"], info
+
+
+def rollout_sharded(policy, env, group=None, reduce_max=None) -> Tuple[torch.Tensor, Dict]:
+    """``rollout`` for one shard of a batch that is split over several ranks (jampr_plus_b200/sharding.py), with the
+    reference's termination semantics for the UNION batch: the reference stops when every rollout of the whole batch
+    is complete (env.py:281) and the reported ``total_cost`` depends on that step (the return legs of vehicles still
+    en route are double counted).  Protocol (include/jampr_b200.h, JAMPR_CTL_HOLD): the shard runs
+    until its own finishing condition and parks; one 4-byte all_reduce(MAX) yields the union's finishing step; the
+    parked step is resumed and the remaining steps are enqueued, so the terminal accounting happens at the same
+    step on every rank.  Tours never depend on this; ``RPEnv.true_cost()`` does not either.
+
+    ``reduce_max``: callable int -> int replacing the collective (tests emulate several ranks in one process)."""
+    from .sharding import global_done_step
+    assert env._is_reset, "call env.reset() or env.import_sol() first"
+    st = env.state
+    st.ensure_policy_buffers(policy.return_logp)
+    w = policy.encode_static(env)
+    ctl = st["ctl"]
+    ctl[_cabi.CTL_HOLD] = 1
+    cap = env.graph_size + env.max_vehicle_number + 1
+    rc = _enqueue(policy, env, w, cap - env._step + 1)
+    local = int(ctl[_cabi.CTL_LOCAL_DONE].item())
+    assert local >= 0, "shard did not reach a finishing condition"
+    final = int(reduce_max(local)) if reduce_max is not None else global_done_step(local, env.device, group)
+    ctl[_cabi.CTL_FINAL_STEP] = final
+    _cabi.check(policy._lib.jampr_env_resume(env._dims, env._inst, st.struct(), int(local), env._stream()),
+                "jampr_env_resume")
+    if final > local:
+        env._step = local + 1
+        env._graph_fresh = (local <= env.max_concurrent_vehicles + 1) or (local % env.tour_graph_update_step == 0)
+        _enqueue(policy, env, w, final - local)
+    done_step = int(ctl[_cabi.CTL_DONE_STEP].item())
+    assert done_step == final, (done_step, final)
+    env._raise_status()
+    env._step = done_step + 1
+    env._has_instance = False
+    env._is_reset = False
+    env._done = True
+    return st["total"], {"done_step": done_step, "local_done_step": local, "steps_enqueued": rc + max(final - local, 0)}
 
 
 def eval_episode(data: List[RPInstance], env, policy, sampling: bool = False, **kwargs):

@@ -400,3 +400,75 @@ def test_config3_sampling_rollouts_properties(precision):
     assert (p0[:, 0:1] != p0[:, 1:]).any(-1).float().mean() > 0.9
     cost, idx, _ = env.gather_best()
     assert torch.isfinite(cost).all() and int(idx.max()) < 128
+
+
+@pytest.mark.parametrize("name,precision", [("g21_pomo", "fp32"), ("g31_k2", "fp32"), ("g21_pomo", "fp16")])
+def test_sharded_rollout_reproduces_union_batch_totals(name, precision):
+    """Two shards of a batch, run as separate environments with the hold / resume protocol of rollout_sharded (the
+    all_reduce emulated in-process), must report the totals of the union batch run in one piece: the reference's
+    total_cost depends on the batch-global finishing step."""
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.driver import rollout, rollout_sharded
+    from jampr_plus_b200.weights import random_state_dict
+    g = load_case(name)
+    env, pol = _make(g, precision=precision)
+    sn = _sn(g)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        env.reset(start_nodes=sn)
+        total_u, info_u = rollout(pol, env)
+        total_u, plan_u = total_u.clone(), env.tour_plan.clone()
+        I, P = len(g["instances"]), env.num_samples
+        cut = I // 2
+        parts, locals_ = [], []
+        for lo, hi in ((0, cut), (cut, I)):
+            e = RPEnv(inference=True, device="cuda", **env_args(g["env_kwargs"]))
+            e.load_data(g["instances"][lo:hi], dist_mat=torch.from_numpy(g["static_dist"][lo:hi]))
+            e.reset(start_nodes=sn[lo * P: hi * P])
+            parts.append(e)
+        # phase 1 on both shards (each parks at its own finishing step), then the emulated all_reduce(MAX)
+        box = {}
+
+        def make_reduce(i):
+            def red(local):
+                box[i] = local
+                return max(box.values()) if len(box) == 2 else None
+            return red
+
+        # run shard 0 up to its parking step by hand to learn its local step, then both properly
+        from jampr_plus_b200 import _cabi
+        for i, e in enumerate(parts):
+            st = e.state
+            st.ensure_policy_buffers(pol.return_logp)
+            w = pol.encode_static(e)
+            st["ctl"][_cabi.CTL_HOLD] = 1
+            cap = e.graph_size + e.max_vehicle_number + 1
+            rc = pol._lib.jampr_rollout(e._dims, e._inst, w, st.struct(), int(e._step), 1, 0, 0, cap - e._step + 1, e._stream())
+            assert rc > 0
+            locals_.append(int(st["ctl"][_cabi.CTL_LOCAL_DONE].item()))
+        final = max(locals_)
+        assert final == info_u["done_step"], "the union batch terminates when its slowest shard does"
+        totals = []
+        for e, local in zip(parts, locals_):
+            st = e.state
+            w = pol.encode_static(e)
+            st["ctl"][_cabi.CTL_FINAL_STEP] = final
+            _cabi.check(pol._lib.jampr_env_resume(e._dims, e._inst, st.struct(), local, e._stream()), "resume")
+            if final > local:
+                fresh = int((local <= e.max_concurrent_vehicles + 1) or (local % e.tour_graph_update_step == 0))
+                rc = pol._lib.jampr_rollout(e._dims, e._inst, w, st.struct(), local + 1, fresh, 0, 0, final - local, e._stream())
+                assert rc == final - local
+            assert int(st["ctl"][_cabi.CTL_DONE_STEP].item()) == final
+            totals.append(st["total"].clone())
+        # and the packaged driver on a fresh copy of shard 0, all_reduce replaced by the known answer
+        e0 = RPEnv(inference=True, device="cuda", **env_args(g["env_kwargs"]))
+        e0.load_data(g["instances"][:cut], dist_mat=torch.from_numpy(g["static_dist"][:cut]))
+        e0.reset(start_nodes=sn[: cut * P])
+        t0, info0 = rollout_sharded(pol, e0, reduce_max=lambda local: final)
+    assert torch.equal(torch.cat([p.tour_plan for p in parts]), plan_u)
+    got = torch.cat(totals)
+    assert len(set(locals_)) >= 1
+    np.testing.assert_allclose(got.cpu().numpy(), total_u.cpu().numpy(), rtol=FINAL_COST_RTOL, atol=0)
+    np.testing.assert_allclose(t0.cpu().numpy(), total_u[: cut * P].cpu().numpy(), rtol=FINAL_COST_RTOL, atol=0)
+    assert info0["done_step"] == final
+    print(f"{name}: shard finishing steps {locals_}, union {final}")
