@@ -242,6 +242,61 @@ int jampr_tc_prepare(const jampr_dims_t* d, const jampr_instances_t* inst, int p
   return launch_status();
 }
 
+// The same mat-vec (8 outputs per thread, one input vector) software-pipelined over batches of eight weight rows:
+// batch i+1 is in flight while batch i is consumed, and the first batch (`pre`) was requested by the caller long
+// before — the weights depend on nothing, only the input vector does.  The chain of five dependent decoder stages
+// is latency-bound on these L2 loads (profiles/r1_policy_step_tc2_ablation.txt).
+template <typename T>
+__device__ __forceinline__ void mv_prefetch(const T* __restrict__ W, int K, uint4 (&pre)[8]) {
+  const int og = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const T* wp = W + (size_t)(ks * (K / 8)) * 256 + og * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)i * 256));
+}
+
+template <typename T>
+__device__ __forceinline__ void mv_consume8(const uint4 (&raw)[8], uint32_t xa, int c0, float (&acc)[8]) {
+  using T2 = typename Elem<T>::T2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 f0 = Elem<T>::to2(from_u32<T2>(raw[i].x)), f1 = Elem<T>::to2(from_u32<T2>(raw[i].y));
+    const float2 f2_ = Elem<T>::to2(from_u32<T2>(raw[i].z)), f3 = Elem<T>::to2(from_u32<T2>(raw[i].w));
+    const float2 xv = f2(lds_f32(xa + (uint32_t)(c0 + i) * 4u));
+    float2 a0 = __ffma2_rn(f0, xv, make_float2(acc[0], acc[1]));
+    float2 a1 = __ffma2_rn(f1, xv, make_float2(acc[2], acc[3]));
+    float2 a2 = __ffma2_rn(f2_, xv, make_float2(acc[4], acc[5]));
+    float2 a3 = __ffma2_rn(f3, xv, make_float2(acc[6], acc[7]));
+    acc[0] = a0.x; acc[1] = a0.y; acc[2] = a1.x; acc[3] = a1.y; acc[4] = a2.x; acc[5] = a2.y; acc[6] = a3.x; acc[7] = a3.y;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void matvec2_pipe(const T* __restrict__ W, int K, uint32_t x_saddr, float* s_part, uint4 (&pre)[8]) {
+  const int og = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const int kn = K / 8, k0 = ks * kn;
+  const T* wp = W + (size_t)k0 * 256 + og * 8;
+  const uint32_t xa = x_saddr + (uint32_t)k0 * 4u;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < kn; c0 += 16) {
+    uint4 nxt[8];
+    if (c0 + 8 < kn) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nxt[i] = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)(c0 + 8 + i) * 256));
+    }
+    mv_consume8<T>(pre, xa, c0, acc);
+    if (c0 + 16 < kn) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)(c0 + 16 + i) * 256));
+    }
+    if (c0 + 8 < kn) mv_consume8<T>(nxt, xa, c0 + 8, acc);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_part[ks * 256 + og * 8 + j] = acc[j];
+}
+
 __host__ __device__ inline uint32_t p2_al(uint32_t b) { return (b + 15u) & ~15u; }
 __host__ __device__ inline uint32_t p2_tile_stride(int N) { return (uint32_t)((N + 7) / 8) * 1024u; }
 // bytes of the region shared by the edge tables (GNN phase) and decoder scratch (decoder phase)
@@ -607,6 +662,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     }
     return;
   }
+  uint4 pre[8];
+  mv_prefetch<T>(w16 + W16_CTXT, 512, pre);          // first weight batch of stage (c): no dependency, hides its latency
   if (mv) matvec2<T, 2, 4>(w16 + W16_TO2, 128, smem_u32(s_mean), 128, s_part);     // NV = 4 >= K slots (K <= 4 here)
   // (a) column mean / max of node_emb over the nodes (policy.py:179-181): thread = column pair x row parity
   {
@@ -643,7 +700,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   __syncthreads();
   // (c) ctxt = ctxt_proj(query)
-  if (mv) matvec2<T, 8, 1>(w16 + W16_CTXT, 512, smem_u32(s_q), 0, s_part);
+  if (mv) matvec2_pipe<T>(w16 + W16_CTXT, 512, smem_u32(s_q), s_part, pre);
+  mv_prefetch<T>(w16 + W16_GK, 256, pre);
   __syncthreads();
   {
     float v = 0.0f;
@@ -653,7 +711,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   __syncthreads();
   // (d) qp[h] = W_gk,h^T ctxt_h : K-slice ks (32 rows of set_proj) belongs to head ks / 2
-  if (mv) matvec2<T, 8, 1>(w16 + W16_GK, 256, smem_u32(s_ctxt), 0, s_part);
+  if (mv) matvec2_pipe<T>(w16 + W16_GK, 256, smem_u32(s_ctxt), s_part, pre);
+  mv_prefetch<T>(w16 + W16_GV, 256, pre);            // consumed after the glimpse softmax: fully hidden
   __syncthreads();
   for (int e = tid; e < 1024; e += P2_THREADS) {
     const int h = e >> 8, c = e & 255;
@@ -762,7 +821,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   __syncthreads();
   // (h) glimpse g[o] = W_gv[o] . gbar[head(o)]
-  if (mv) matvec2<T, 8, 1>(w16 + W16_GV, 256, smem_u32(s_gbar) + (uint32_t)((tid & 31) >> 3) * QP2_STRIDE * 4u, 0, s_part);
+  if (mv) matvec2_pipe<T>(w16 + W16_GV, 256, smem_u32(s_gbar) + (uint32_t)((tid & 31) >> 3) * QP2_STRIDE * 4u, s_part, pre);
+  mv_prefetch<T>(w16 + W16_M1, 256, pre);
   __syncthreads();
   {
     float v = 0.0f;
@@ -772,7 +832,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   __syncthreads();
   // (i) lp = W_lk^T out_proj(g) = M1 g
-  if (mv) matvec2<T, 8, 1>(w16 + W16_M1, 256, smem_u32(s_g), 0, s_part);
+  if (mv) matvec2_pipe<T>(w16 + W16_M1, 256, smem_u32(s_g), s_part, pre);
   __syncthreads();
   {
     float v = 0.0f;
