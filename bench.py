@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--instances", type=int, default=4096, help="instances per GPU (config 2: 4096)")
     ap.add_argument("--precision", default=os.environ.get("JAMPR_PRECISION", "fp16"), choices=["fp32", "bf16", "fp16"])
-    ap.add_argument("--cpu-sample", type=int, default=4, help="instances of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=12, help="instances of the CPU baseline sample (x16 samples; ~14 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -68,17 +68,20 @@ __device__ __forceinline__ void gemm128(float (&acc)[TM][8], const float* A0, co
       for (int k4 = 0; k4 < 4; ++k4) {
         const float4 w0 = *reinterpret_cast<const float4*>(wb + (kk + k4) * 128 + tx * 4);
         const float4 w1 = *reinterpret_cast<const float4*>(wb + (kk + k4) * 128 + 64 + tx * 4);
+        const float2 w00 = make_float2(w0.x, w0.y), w01 = make_float2(w0.z, w0.w);
+        const float2 w10 = make_float2(w1.x, w1.y), w11 = make_float2(w1.z, w1.w);
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
+          // packed fp32 FMA (FFMA2, sm_100): each component is the same IEEE fma as the scalar form, at twice the
+          // issue rate of the three-register FFMA
           const float av = f4_get(a[i], k4);
-          acc[i][0] = fmaf(av, w0.x, acc[i][0]);
-          acc[i][1] = fmaf(av, w0.y, acc[i][1]);
-          acc[i][2] = fmaf(av, w0.z, acc[i][2]);
-          acc[i][3] = fmaf(av, w0.w, acc[i][3]);
-          acc[i][4] = fmaf(av, w1.x, acc[i][4]);
-          acc[i][5] = fmaf(av, w1.y, acc[i][5]);
-          acc[i][6] = fmaf(av, w1.z, acc[i][6]);
-          acc[i][7] = fmaf(av, w1.w, acc[i][7]);
+          const float2 a2 = make_float2(av, av);
+          float2 r0 = __ffma2_rn(a2, w00, make_float2(acc[i][0], acc[i][1]));
+          float2 r1 = __ffma2_rn(a2, w01, make_float2(acc[i][2], acc[i][3]));
+          float2 r2 = __ffma2_rn(a2, w10, make_float2(acc[i][4], acc[i][5]));
+          float2 r3 = __ffma2_rn(a2, w11, make_float2(acc[i][6], acc[i][7]));
+          acc[i][0] = r0.x; acc[i][1] = r0.y; acc[i][2] = r1.x; acc[i][3] = r1.y;
+          acc[i][4] = r2.x; acc[i][5] = r2.y; acc[i][6] = r3.x; acc[i][7] = r3.y;
         }
       }
     }
