@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   float* s_feat = reinterpret_cast<float*>(take((uint32_t)K * 8 * 4));
   int* s_nbh = reinterpret_cast<int*>(take((uint32_t)A * 4));
   int8_t* s_pos = reinterpret_cast<int8_t*>(take((uint32_t)K * N));    // slot t, node n -> candidate index j or -1
+  int16_t* s_cand = reinterpret_cast<int16_t*>(take((uint32_t)N * 2));  // nodes that are a candidate of some slot, ascending
   uint8_t* s_mask = take(A);
   int* s_idx = reinterpret_cast<int*>(take(JAMPR_MAX_SLOTS * 4));
   // region R2 during the GNN: edge tables
@@ -454,6 +455,21 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   tc_fence_after();
 
   const int q4 = warp & 3, ch = warp >> 2, r = q4 * 32 + lane;      // epilogue role: row r, columns 64ch..64ch+63
+  if (warp == 1) {
+    // compact list of the distinct candidate nodes in ascending order (deterministic): the decoder's per-node dot
+    // products and weighted sums only visit these (typically 50..70 of the 101 nodes)
+    int cnt = 0;
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      const int n = n0 + lane;
+      bool is = false;
+      if (n < N)
+        for (int t = 0; t < K; ++t) is |= s_pos[t * N + n] >= 0;
+      const unsigned m = __ballot_sync(0xffffffffu, is);
+      if (is) s_cand[cnt + __popc(m & ((1u << lane) - 1u))] = (int16_t)n;
+      cnt += __popc(m);
+    }
+    if (lane == 0) s_cnt[2] = cnt;
+  }
 
   if (fresh) {
     const uint32_t tmem = *tmem_slot;
@@ -727,7 +743,9 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     for (int h = 0; h < 4; ++h)
 #pragma unroll
       for (int i = 0; i < 4; ++i) qv[h][i] = *reinterpret_cast<const float2*>(s_qp + h * QP2_STRIDE + 2 * (lane + 32 * i));
-    for (int n = warp; n < N + K; n += P2_WARPS) {
+    const int nc = s_cnt[2];
+    for (int i = warp; i < nc + K; i += P2_WARPS) {
+      const int n = i < nc ? (int)s_cand[i] : N + (i - nc);
       float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -792,7 +810,9 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     const int c2 = tid & 127, half = tid >> 7;
     const uint32_t pn_saddr = smem_u32(s_pn4);
     float2 g0 = make_float2(0.0f, 0.0f), g1 = g0, g2 = g0, g3 = g0;
-    for (int n = half; n < N; n += 2) {
+    const int nc = s_cnt[2];
+    for (int i = half; i < nc; i += 2) {
+      const int n = s_cand[i];
       const float2 v = Elem<T>::to2(*reinterpret_cast<const T2*>(s_ne16 + (size_t)n * NE16_STRIDE + c2 * 4));
       const float4 pw = lds_f32x4(pn_saddr + (uint32_t)n * 16u);
       g0 = __ffma2_rn(f2(pw.x), v, g0);
@@ -846,7 +866,9 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     float2 lv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) lv[i] = *reinterpret_cast<const float2*>(s_lp + 2 * (lane + 32 * i));
-    for (int n = warp; n < N + K; n += P2_WARPS) {
+    const int nc = s_cnt[2];
+    for (int i = warp; i < nc + K; i += P2_WARPS) {
+      const int n = i < nc ? (int)s_cand[i] : N + (i - nc);
       float dd = 0.0f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -938,7 +960,7 @@ static size_t p2_smem_bytes(const jampr_dims_t* d) {
   size_t s = 1024 + 4 * (size_t)p2_tile_stride(N) + P2_R1_BYTES + p2_r2_bytes(N, k, A);
   s += p2_al(32) + p2_al(16) + p2_al(2 * 128 * 8) + p2_al(384 * 4) + p2_al(16) + p2_al(K * L * 2);
   s += 2 * p2_al(4 * JAMPR_MAX_SLOTS * 4) + p2_al(JAMPR_MAX_SLOTS * 4) + p2_al(K * 8 * 4) + p2_al(A * 4) + p2_al(K * N) + p2_al(A) +
-       p2_al(JAMPR_MAX_SLOTS * 4);
+       p2_al(JAMPR_MAX_SLOTS * 4) + p2_al(N * 2);
   return s;
 }
 
