@@ -45,6 +45,24 @@ __device__ __forceinline__ bool jampr_step_active(const int32_t* ctl, int step_n
   return true;
 }
 
+// A rollout whose customers are all served and whose vehicles are all back at the depot can only make zero-cost
+// depot -> depot moves until the batch terminates (env.py:281: lockstep over the batch): no state changes whichever
+// slot the policy picks.  The fused device loop skips the policy for such rollouts and emits action (slot 0, depot);
+// callers that want the log-probabilities (st.logp set: step API of the parity tests) still get the full forward.
+__device__ __forceinline__ bool jampr_rollout_idle(const jampr_state_t& st, int b, int K) {
+  if (st.logp != nullptr || !st.allvis[b]) return false;
+  for (int t = 0; t < K; ++t)
+    if (st.cur[(size_t)b * K + t] != 0) return false;
+  return true;
+}
+// same test with the all-visited flag already in hand (loaded next to the control word, off the critical path)
+__device__ __forceinline__ bool jampr_rollout_idle2(const jampr_state_t& st, int b, int K, uint8_t allvis) {
+  if (!allvis) return false;
+  for (int t = 0; t < K; ++t)
+    if (st.cur[(size_t)b * K + t] != 0) return false;
+  return true;
+}
+
 // Counter-based uniform in [0,1): splitmix64 of (seed, rollout, step). Restated in
 // oracle/rng.py so that sampling runs can be replayed on the CPU.
 __host__ __device__ __forceinline__ float jampr_uniform(uint64_t seed, uint32_t rollout, uint32_t step) {

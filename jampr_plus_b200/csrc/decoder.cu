@@ -32,6 +32,15 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decoder_kernel(const DecArgs a
   if (!jampr_step_active(st.ctl, a.step_no)) return;
   const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh, A = K * k, L = d.plan_len;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (jampr_rollout_idle(st, b, K)) {
+    if (tid == 0) {
+      st.action[2 * (size_t)b] = 0;
+      st.action[2 * (size_t)b + 1] = 0;
+      st.ll[b] = 0.0f;
+      st.entropy[b] = 0.0f;
+    }
+    return;
+  }
   const float* __restrict__ w = a.w;
 
   float* s_act = dsm;                         // [A][256]

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_layer_kernel(const LgArgs a)
   const jampr_state_t& st = a.st;
   if (!a.per_instance) {
     if (!jampr_step_active(st.ctl, a.step_no)) return;
+    if (jampr_rollout_idle(st, blockIdx.y, d.n_slots)) return;
   }
   const int N = d.n_nodes, k = d.k_nbh, k4 = (k + 3) & ~3;
   const int tile = blockIdx.x, g = blockIdx.y, npad = gridDim.x * 128;
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_proj_kernel(const LgArgs a, 
   const jampr_instances_t& p = a.p;
   if (!a.per_instance) {
     if (!jampr_step_active(a.st.ctl, a.step_no)) return;
+    if (jampr_rollout_idle(a.st, blockIdx.y, d.n_slots)) return;
   }
   const int N = d.n_nodes;
   const int tile = blockIdx.x, g = blockIdx.y, npad = gridDim.x * 128;

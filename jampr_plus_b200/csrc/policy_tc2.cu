@@ -316,11 +316,21 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   const jampr_dims_t& d = a.d;
   const jampr_state_t& st = a.st;
   const jampr_instances_t& p = a.p;
+  const uint8_t allvis_b = st.logp ? (uint8_t)0 : st.allvis[blockIdx.x];     // issued together with the control word
   if (!jampr_step_active(st.ctl, a.step_no)) return;
   const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh, A = K * k, L = d.plan_len;
   const int k4 = (k + 3) & ~3, nd = (N + 7) & ~7;
   const int b = blockIdx.x, ins = b / d.n_samples;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (jampr_rollout_idle2(st, b, K, allvis_b)) {
+    if (tid == 0) {
+      st.action[2 * (size_t)b] = 0;
+      st.action[2 * (size_t)b + 1] = 0;
+      st.ll[b] = 0.0f;
+      st.entropy[b] = 0.0f;
+    }
+    return;
+  }
   const float* __restrict__ w = a.w;
   const T* __restrict__ w16 = reinterpret_cast<const T*>(a.w16);
   const bool fresh = a.graph_fresh != 0;
@@ -402,7 +412,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     }
     __syncwarp();
     if (warp == 0) tmem_alloc(tmem_slot, 256);
-    for (uint32_t e = tid; e < (4 * ts) / 16; e += P2_THREADS) reinterpret_cast<uint4*>(sA)[e] = make_uint4(0u, 0u, 0u, 0u);
+    // operand rows >= N are never initialised: the MMA reads them, but they only feed accumulator rows >= N, which
+    // nothing reads (rows are independent in every later phase)
   }
   if (tid < 4) s_cnt[tid] = 0;
   for (int e = tid; e < K * N; e += P2_THREADS) s_pos[e] = (int8_t)-1;
@@ -600,9 +611,11 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     // The static_emb rows come from L2: chunk c+1 is in flight while chunk c is combined; chunk 0 is requested
     // before the wait for the projection MMAs.
     const float4* se_row = reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + min(r, N - 1)) * 256 + ch * 128);
-    float4 sv[8];
+    float4 sv0[8], sv1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sv[i] = __ldg(se_row + i);
+    for (int i = 0; i < 8; ++i) sv0[i] = __ldg(se_row + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sv1[i] = __ldg(se_row + 8 + i);
     if (tid == 0) mbar_wait(bar_acc, 0u);
     __syncthreads();          // projection complete and per-tour means done: the h tiles may be overwritten
     tc_fence_after();
@@ -611,14 +624,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       const int col0 = ch * 128 + c * 32;
       uint32_t acc[32];
       tmem_ld32_nowait(ta + col0, acc);
-      float4 cur[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = sv[i];
-      if (c < 3) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sv[i] = __ldg(se_row + (c + 1) * 8 + i);
-      }
       tmem_wait_ld();
+      float4 (&cur)[8] = (c & 1) ? sv1 : sv0;
       if (r < N) {
         const float4* bo = reinterpret_cast<const float4*>(w + OFF_TE_OUT_B + col0);
         float4* gdst = a.store_cache ? reinterpret_cast<float4*>(st.ne + ((size_t)b * N + r) * 256 + col0) : nullptr;
@@ -635,6 +642,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
                          as_u32(Elem<T>::from2(vb.x, vb.y)), as_u32(Elem<T>::from2(vb.z, vb.w)));
           if (gdst) { gdst[2 * i] = va; gdst[2 * i + 1] = vb; }
         }
+      }
+      if (c < 2) {          // refill this buffer with the chunk two ahead: in flight during the next chunk
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = __ldg(se_row + (c + 2) * 8 + i);
       }
     }
     tc_fence_before();
