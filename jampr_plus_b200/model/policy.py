@@ -148,6 +148,15 @@ class Policy(nn.Module):
                 m.reset_parameters()
         self._blob_key = None
 
+    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
+        """Accepts the reference checkpoint schema (tests/golden/state_dict_schema.json); the GraphConv linears may
+        carry the older PyG names ``conv.lin_l`` / ``conv.lin_r``.  Anything else fails loudly (strict)."""
+        from ..weights import canonical_key
+        sd = type(state_dict)((canonical_key(k), v) for k, v in state_dict.items())
+        out = super().load_state_dict(sd, strict=strict, **kwargs)
+        self._blob_key = None
+        return out
+
     def reset_static(self):
         """Forget the node-encoder output (policy.py:162-165)."""
         self.static_node_emb = None

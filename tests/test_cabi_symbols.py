@@ -89,3 +89,23 @@ def test_policy_state_dict_schema_matches_reference():
     got = {k: list(v.shape) for k, v in pol.state_dict().items()}
     assert list(got.keys()) == list(sch.keys())
     assert got == sch
+
+
+def test_policy_refuses_cpu_and_checks_schema():
+    """No fallback path: constructing the mirrors needs the library, running them needs CUDA; load_state_dict accepts
+    the reference schema (old PyG aliases included) and nothing else."""
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.weights import random_state_dict
+    with pytest.raises(RuntimeError):
+        RPEnv(device="cpu")
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cpu")      # parameter container only; forward needs a CUDA env
+    sd = random_state_dict(2)
+    alias = {k.replace(".conv.lin_rel.", ".conv.lin_l.").replace(".conv.lin_root.", ".conv.lin_r."): v for k, v in sd.items()}
+    pol.load_state_dict(alias)
+    assert torch.equal(pol.state_dict()["node_encoder.layers.0.conv.lin_rel.weight"], sd["node_encoder.layers.0.conv.lin_rel.weight"])
+    bad = dict(sd)
+    bad["decoder.extra.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        pol.load_state_dict(bad)
+    with pytest.raises(NotImplementedError):
+        Policy(RPEnv.OBSERVATION_SPACE, device="cpu", embedding_dim=128)
