@@ -255,7 +255,7 @@ def main():
     done_step = int(env.state["ctl"][_cabi.CTL_DONE_STEP].item())
     status_bits = int(env.state["status"].max().item())
     assert done_step >= 0, "episode did not terminate"
-    assert not (status_bits & (_cabi.ST_NO_FEASIBLE | _cabi.ST_TOUR_OVERFLOW | _cabi.ST_NAN_LOGITS)), status_bits
+    assert os.environ.get("JAMPR_TC_ABLATE") or not (status_bits & (_cabi.ST_NO_FEASIBLE | _cabi.ST_TOUR_OVERFLOW | _cabi.ST_NAN_LOGITS)), status_bits
 
     clocks = ClockSampler(local)
     if rank == 0:

@@ -534,8 +534,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       const bool proj = (l == 6);
       if (tid == 0) {
         // first weight pair: lin_root(h) (K-blocks 2,3) — or W_o rows 0..127 — overlaps the aggregation below
-        mbar_wait(&full[0], 0u);
-        mbar_wait(&full[1], 0u);
+        if (!ABL(32)) {
+          mbar_wait(&full[0], 0u);
+          mbar_wait(&full[1], 0u);
+        }
         tc_fence_after();
         if (!(ABL(8))) {
           mma_kblock(tmem, a_addr + 2 * ts, w_addr, idesc, true);
@@ -577,8 +579,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         }
       }
       if (tid == 0) {
-        mbar_wait(&full[0], 1u);
-        mbar_wait(&full[1], 1u);
+        if (!ABL(32)) {
+          mbar_wait(&full[0], 1u);
+          mbar_wait(&full[1], 1u);
+        }
         tc_fence_after();
         if (ABL(8)) {
         } else if (!proj) {

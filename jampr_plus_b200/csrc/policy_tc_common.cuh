@@ -29,7 +29,7 @@ struct PtArgs {
   int graph_fresh;
   int store_cache;       // write h_fin / ne / ne_stats to HBM (needed when later steps reuse them)
   int ablate;            // timing experiments only (JAMPR_TC_ABLATE): 1 skip kNN aggregation, 2 skip layer epilogue
-                         // math, 4 skip the decoder mat-vec chain, 8 skip the MMAs, 16 skip the whole decoder
+                         // math, 4 skip the decoder mat-vec chain, 8 skip the MMAs, 16 skip the whole decoder, 32 no wait for weight stages
 };
 
 template <typename T>
