@@ -48,7 +48,7 @@ def rollout(policy, env, max_steps: Optional[int] = None, check: bool = True,
         g = _GRAPHS.get(key)
         if g is None:
             rc = _enqueue(policy, env, w, n)            # eager first run (also sets the kernels' smem attributes)
-            if len(_GRAPHS) > 64:
+            if len(_GRAPHS) > 512:     # e.g. one graph per start step of the LNS repair rollouts
                 _GRAPHS.clear()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):                  # capture launches nothing: the eager run above is the result
