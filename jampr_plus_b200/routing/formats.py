@@ -11,20 +11,23 @@ import torch
 
 __all__ = ["RPInstance", "RPObs"]
 
+_Array = Union[np.ndarray, torch.Tensor]
+_Scalar = Union[float, int]
+
 
 class RPInstance(NamedTuple):
-    coords: Union[np.ndarray, torch.Tensor]          # (N, 2) in [0, 1]^2, row 0 = depot
-    demands: Union[np.ndarray, torch.Tensor]         # (N,) normalised by vehicle capacity
-    tw: Union[np.ndarray, torch.Tensor]              # (N, 2) normalised by service horizon
-    service_time: Union[np.ndarray, torch.Tensor, float]
-    graph_size: int
-    org_service_horizon: Union[float, int]
-    max_vehicle_number: int
-    vehicle_capacity: float = 1.0
-    service_horizon: float = 1.0
-    depot_idx: List = [0]
-    type: Union[int, str] = ""
-    tw_frac: Union[float, str] = ""
+    coords: _Array                           # (N, 2) in [0, 1]^2, row 0 = depot
+    demands: _Array                          # (N,) normalised by vehicle capacity
+    tw: _Array                               # (N, 2) normalised by service horizon
+    service_time: Union[_Array, float]       # one value per instance (all customers share it)
+    graph_size: int                          # N, depot included
+    org_service_horizon: _Scalar             # depot due date in original units (cost un-normalisation)
+    max_vehicle_number: int                  # fleet size kv; the env uses K_max = kv + floor(ln kv)
+    vehicle_capacity: float = 1.0            # always 1 after normalisation
+    service_horizon: float = 1.0             # always 1 after normalisation
+    depot_idx: List = [0]                    # the depot is node 0
+    type: Union[int, str] = ""               # Solomon type "1" / "2" (selects the checkpoint family)
+    tw_frac: Union[float, str] = ""          # fraction of customers with a real time window
 
     def __getitem__(self, key):
         # reference instances are indexed by field name (env.py:1031-1033)
@@ -40,7 +43,7 @@ class RPInstance(NamedTuple):
 
 
 class RPObs(NamedTuple):
-    batch_size: int
+    batch_size: int                   # number of rollouts (instances x samples)
     node_features: torch.Tensor       # (bs, N, 7) f32
     node_nbh_edges: torch.Tensor      # (2, bs*(N + (N-1)k)) i64 running index
     node_nbh_weights: torch.Tensor    # (bs*(N + (N-1)k),) f32
