@@ -35,14 +35,14 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 
 // Is the kernel launched for env._step == step_no still live?  Not after the episode terminated (env.py:281), and
 // not while a sharded run is parked at its local finishing step waiting for the global one (JAMPR_CTL_HOLD).
-__device__ __forceinline__ bool jampr_step_active(const int32_t* ctl, int step_no) {
-  const int done_step = ctl[JAMPR_CTL_DONE_STEP];
+__device__ __forceinline__ bool jampr_step_active_w(int done_step, int hold, int fin, int ld, int step_no) {
   if (done_step >= 0 && done_step < step_no) return false;
-  if (ctl[JAMPR_CTL_HOLD] != 0 && ctl[JAMPR_CTL_FINAL_STEP] < 0) {
-    const int ld = ctl[JAMPR_CTL_LOCAL_DONE];
-    if (ld >= 0 && ld < step_no) return false;
-  }
+  if (hold != 0 && fin < 0 && ld >= 0 && ld < step_no) return false;
   return true;
+}
+__device__ __forceinline__ bool jampr_step_active(const int32_t* ctl, int step_no) {
+  return jampr_step_active_w(ctl[JAMPR_CTL_DONE_STEP], ctl[JAMPR_CTL_HOLD], ctl[JAMPR_CTL_FINAL_STEP],
+                             ctl[JAMPR_CTL_LOCAL_DONE], step_no);
 }
 
 // A rollout whose customers are all served and whose vehicles are all back at the depot can only make zero-cost

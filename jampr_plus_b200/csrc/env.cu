@@ -13,27 +13,30 @@ struct Roll {
   int b, ins, lane;
 };
 
-// ---- one transition, executed by lane 0 (A.4 steps 1-5). Returns the step cost.
+// ---- one transition, executed by one thread (A.4 steps 1-5). Returns the step cost.
+// Every load is issued before the first store: the kernel is a chain of dependent HBM round trips, and the only
+// true dependency is action -> slot state -> dist[prev][node].
 __device__ float env_apply_move(const jampr_dims_t& d, const jampr_instances_t& p, const jampr_state_t& s,
-                                int b, int ins, int slot, int node) {
+                                int b, int ins, int slot, int node, int* nvis_after = nullptr) {
   const int N = d.n_nodes, K = d.n_slots, L = d.plan_len;
-  const size_t bk = (size_t)b * K + slot;
+  const size_t bk = (size_t)b * K + slot, in = (size_t)ins * N + node, bn = (size_t)b * N + node;
   const int prev = s.cur[bk];
-  s.cur[bk] = node;
-  s.cap[bk] = __fsub_rn(s.cap[bk], p.demand[(size_t)ins * N + node]);
+  const float cap0 = s.cap[bk], t0 = s.time[bk], cttd0 = s.cttd[bk];
+  const int r = s.row[bk], pos = s.nxt[bk], last = s.row_last[bk];
+  const float dem = p.demand[in], tw_open = p.tw[in * 2], ttd_new = p.ttd[in], service = p.service[ins];
+  const uint8_t seen = s.visited[bn];
+  const int nvis0 = s.nvis[b];
   float delta = p.dist[((size_t)ins * N + prev) * N + node];
-  const float t0 = s.time[bk];
+  s.cur[bk] = node;
+  s.cap[bk] = __fsub_rn(cap0, dem);
   const float arrival = __fadd_rn(t0, delta);
   if (node != 0) {
-    const float wait = fmaxf(__fsub_rn(p.tw[((size_t)ins * N + node) * 2], arrival), 0.0f);
-    delta = __fadd_rn(delta, __fadd_rn(wait, p.service[ins]));
+    const float wait = fmaxf(__fsub_rn(tw_open, arrival), 0.0f);
+    delta = __fadd_rn(delta, __fadd_rn(wait, service));
   }
   s.time[bk] = __fadd_rn(t0, delta);
-  const float ttd_new = p.ttd[(size_t)ins * N + node];
-  const float cost = __fadd_rn(delta, __fsub_rn(ttd_new, s.cttd[bk]));
+  const float cost = __fadd_rn(delta, __fsub_rn(ttd_new, cttd0));
   s.cttd[bk] = ttd_new;
-  const int r = s.row[bk];
-  const int pos = s.nxt[bk];
   if (pos >= L) {
     s.status[b] |= JAMPR_ST_TOUR_OVERFLOW;
   } else {
@@ -41,16 +44,15 @@ __device__ float env_apply_move(const jampr_dims_t& d, const jampr_instances_t& 
   }
   if (node != 0) {
     s.nxt[bk] = pos + 1;
-    const int last = s.row_last[bk];
-    s.pred[(size_t)b * N + node] = (int16_t)last;
+    s.pred[bn] = (int16_t)last;
     if (last != 0) s.succ[(size_t)b * N + last] = (int16_t)node;
     s.row_last[bk] = node;
-    uint8_t* v = s.visited + (size_t)b * N + node;
-    if (!*v) {
-      *v = 1;
-      s.nvis[b] += 1;
+    if (!seen) {
+      s.visited[bn] = 1;
+      s.nvis[b] = nvis0 + 1;
     }
   }
+  if (nvis_after) *nvis_after = nvis0 + ((node != 0 && !seen) ? 1 : 0);
   return cost;
 }
 
@@ -62,74 +64,175 @@ __device__ __forceinline__ int env_next_free(const jampr_dims_t& d, const jampr_
   return 0;
 }
 
-// ---- observation: candidate sets + masks for the K slots of rollout b (whole warp)
-__device__ void env_observe(const jampr_dims_t& d, const jampr_instances_t& p, const jampr_state_t& s,
-                            int b, int ins, int lane, int16_t* dep /* smem [k] */) {
+// ---- observation: candidate sets + masks for the K slots of rollout b (whole warp).
+// Written for memory-level parallelism: a warp's latency is a chain of three HBM/L2 round trips, each link issuing
+// all of its independent loads together:
+//   link 1 (env_obs_prefetch, issued by the kernels next to their control-word loads): counters, slot state,
+//          vehicle flags, the first 128 entries of the depot order;
+//   link 2: visited flags of those entries (depot scan) + kNN candidate ids of the vehicles en route;
+//   link 3: the per-candidate gathers (visited, demand, distance, window close) of four slots at a time.
+struct ObsPre {
+  int nvis, cur, nfin, first_free;
+  float cap, tm;
+  int ord[4];
+};
+
+__device__ __forceinline__ ObsPre env_obs_prefetch(const jampr_dims_t& d, const jampr_instances_t& p,
+                                                   const jampr_state_t& s, int b, int ins, int lane) {
+  const int N = d.n_nodes, K = d.n_slots;
+  ObsPre o;
+  o.nvis = s.nvis[b];
+  o.cur = 1;
+  o.cap = 0.0f;
+  o.tm = 0.0f;
+  if (lane < K) {
+    const size_t bk = (size_t)b * K + lane;
+    o.cur = s.cur[bk];
+    o.cap = s.cap[bk];
+    o.tm = s.time[bk];
+  }
+  const int16_t* ord = p.order + (size_t)ins * N;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int q = 32 * c + lane;
+    o.ord[c] = (q < N) ? (int)ord[q] : 0;
+  }
+  const uint8_t* f = s.vflags + (size_t)b * d.k_max;
+  o.nfin = 0;
+  o.first_free = 0x7fffffff;
+  for (int v = lane; v < d.k_max; v += 32) {
+    const uint8_t fl = f[v];
+    o.nfin += (fl >> 1) & 1;
+    if (fl == 0) o.first_free = min(o.first_free, v);
+  }
+  return o;
+}
+
+__device__ void env_obs_run(const jampr_dims_t& d, const jampr_instances_t& p, const jampr_state_t& s,
+                            int b, int ins, int lane, int16_t* dep /* smem [k] */, const ObsPre& o) {
   const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh;
+  // per-warp base pointers once, 32-bit offsets inside the rows
   const uint8_t* vis = s.visited + (size_t)b * N;
-  const bool allvis = s.nvis[b] == N - 1;
-  bool any_depot = false;
-  for (int t = 0; t < K; ++t) any_depot |= (s.cur[(size_t)b * K + t] == 0);
+  const int16_t* knn = p.knn + (size_t)ins * N * k;
+  const float* demand_i = p.demand + (size_t)ins * N;
+  const float* dist_i = p.dist + (size_t)ins * N * N;
+  const float* tw_i = p.tw + (size_t)ins * N * 2;
+  int16_t* nbh_b = s.nbh + (size_t)b * K * k;
+  uint8_t* mask_b = s.mask + (size_t)b * K * k;
+  const bool allvis = o.nvis == N - 1;
+  const bool any_depot = __any_sync(0xffffffffu, lane < K && o.cur == 0);
+  // link 2
+  int cur0[4], kn0[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    cur0[i] = __shfl_sync(0xffffffffu, o.cur, min(i, K - 1));
+    kn0[i] = 0;
+    if (lane < k && i < K && cur0[i] != 0) kn0[i] = knn[cur0[i] * k + lane];
+  }
   if (any_depot) {
     // first k unvisited nodes in depot order (the depot never counts as visited), padded with the
-    // earliest visited ones, overall order kept (env.py:863-887)
+    // earliest visited ones, overall order kept (env.py:863-887); 128 positions per pass
     const int16_t* ord = p.order + (size_t)ins * N;
-    const int n_unv = N - s.nvis[b];
+    const int n_unv = N - o.nvis;
     const int missing = max(k - n_unv, 0);
+    const unsigned lt = (1u << lane) - 1u;
     int ru = 0, rv = 0, outp = 0;
-    for (int base = 0; base < N && outp < k; base += 32) {
-      const int q = base + lane;
-      int node = 0;
-      bool unv = false, valid = q < N;
-      if (valid) {
-        node = ord[q];
-        unv = !vis[node];
+    for (int base = 0; base < N && outp < k; base += 128) {
+      int node[4];
+      bool unv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int q = base + 32 * c + lane;
+        node[c] = (base == 0) ? o.ord[c] : ((q < N) ? (int)ord[q] : 0);
       }
-      const unsigned mu = __ballot_sync(0xffffffffu, valid && unv);
-      const unsigned mv = __ballot_sync(0xffffffffu, valid && !unv);
-      const unsigned lt = (1u << lane) - 1u;
-      const int my_ru = ru + __popc(mu & lt) + 1;   // inclusive rank among unvisited
-      const int my_rv = rv + __popc(mv & lt) + 1;
-      const bool pick = valid && ((unv && my_ru <= k) || (!unv && my_rv <= missing));
-      const unsigned mp = __ballot_sync(0xffffffffu, pick);
-      if (pick) {
-        const int o = outp + __popc(mp & lt);
-        if (o < k) dep[o] = (int16_t)node;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) unv[c] = vis[node[c]] == 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool valid = base + 32 * c + lane < N;
+        const unsigned mu = __ballot_sync(0xffffffffu, valid && unv[c]);
+        const unsigned mv = __ballot_sync(0xffffffffu, valid && !unv[c]);
+        const int my_ru = ru + __popc(mu & lt) + 1;   // inclusive rank among unvisited
+        const int my_rv = rv + __popc(mv & lt) + 1;
+        const bool pick = valid && ((unv[c] && my_ru <= k) || (!unv[c] && my_rv <= missing));
+        const unsigned mp = __ballot_sync(0xffffffffu, pick);
+        if (pick) {
+          const int q = outp + __popc(mp & lt);
+          if (q < k) dep[q] = (int16_t)node[c];
+        }
+        ru += __popc(mu);
+        rv += __popc(mv);
+        outp += __popc(mp);
       }
-      ru += __popc(mu);
-      rv += __popc(mv);
-      outp += __popc(mp);
     }
     __syncwarp();
   }
   bool mask_depot = false;
   if (!allvis) {
-    int nfin = 0;
-    const uint8_t* f = s.vflags + (size_t)b * d.k_max;
-    for (int v = lane; v < d.k_max; v += 32) nfin += (f[v] >> 1) & 1;
-    nfin = warp_sum_i(nfin);
-    mask_depot = (nfin < K) || (env_next_free(d, s, b) != 0);
+    const int nfin = warp_sum_i(o.nfin);
+    int first_free = o.first_free;
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) first_free = min(first_free, __shfl_xor_sync(0xffffffffu, first_free, sh));
+    // first tour row that is neither finished nor active, if any and not row 0 (env.py:1035-1040)
+    mask_depot = (nfin < K) || (first_free != 0x7fffffff && first_free != 0);
   }
-  for (int t = 0; t < K; ++t) {
-    const size_t bk = (size_t)b * K + t;
-    const int cur = s.cur[bk];
-    const float cap = s.cap[bk], tm = s.time[bk];
-    const int16_t* src = (cur == 0) ? dep : (p.knn + ((size_t)ins * N + cur) * k);
-    const float* drow = p.dist + ((size_t)ins * N + cur) * N;
-    bool all_masked = true;
-    for (int j = lane; j < k; j += 32) {
-      const int n = src[j];
-      bool m = vis[n] != 0;
-      m |= cap < p.demand[(size_t)ins * N + n];
-      m |= __fadd_rn(tm, drow[n]) > p.tw[((size_t)ins * N + n) * 2 + 1];
-      if (cur == 0 && j == 0 && mask_depot) m = true;
-      s.nbh[bk * k + j] = (int16_t)n;
-      s.mask[bk * k + j] = m ? 1 : 0;
-      all_masked &= m;
+  unsigned open_bits = 0u;       // bit t: this lane saw a feasible candidate of slot t
+  for (int j0 = 0; j0 < k; j0 += 32) {
+    const int j = j0 + lane;
+    const bool valid = j < k;
+    for (int tb = 0; tb < K; tb += 4) {
+      const bool first = (j0 | tb) == 0;
+      int cur[4], n[4];
+      float cap[4], tm[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = min(tb + i, K - 1);
+        cur[i] = __shfl_sync(0xffffffffu, o.cur, t);
+        cap[i] = __shfl_sync(0xffffffffu, o.cap, t);
+        tm[i] = __shfl_sync(0xffffffffu, o.tm, t);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        n[i] = 0;
+        if (valid && tb + i < K) {
+          if (cur[i] == 0) n[i] = dep[j];
+          else n[i] = first ? kn0[i] : (int)knn[cur[i] * k + j];
+        }
+      }
+      // link 3
+      uint8_t vs[4];
+      float dm[4], dr[4], tc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        vs[i] = vis[n[i]];
+        dm[i] = demand_i[n[i]];
+        dr[i] = dist_i[cur[i] * N + n[i]];
+        tc[i] = tw_i[n[i] * 2 + 1];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (valid && tb + i < K) {
+          const int e = (tb + i) * k + j;
+          bool m = vs[i] != 0;
+          m |= cap[i] < dm[i];
+          m |= __fadd_rn(tm[i], dr[i]) > tc[i];
+          if (cur[i] == 0 && j == 0 && mask_depot) m = true;
+          nbh_b[e] = (int16_t)n[i];
+          mask_b[e] = m ? 1 : 0;
+          if (!m) open_bits |= 1u << (tb + i);
+        }
+      }
     }
-    all_masked = __all_sync(0xffffffffu, all_masked);
-    if (all_masked && lane == 0) s.status[b] |= JAMPR_ST_NO_FEASIBLE;
   }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) open_bits |= __shfl_xor_sync(0xffffffffu, open_bits, sh);
+  if (lane == 0 && open_bits != ((1u << K) - 1u)) s.status[b] |= JAMPR_ST_NO_FEASIBLE;
+}
+
+__device__ __forceinline__ void env_observe(const jampr_dims_t& d, const jampr_instances_t& p, const jampr_state_t& s,
+                                            int b, int ins, int lane, int16_t* dep) {
+  const ObsPre o = env_obs_prefetch(d, p, s, b, ins, lane);
+  env_obs_run(d, p, s, b, ins, lane, dep, o);
 }
 
 // ---- reset: zero slot state, K active vehicles, forced start moves, first observation
@@ -178,12 +281,17 @@ __global__ void __launch_bounds__(ENV_THREADS) env_move_kernel(jampr_dims_t d, j
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int bs = d.n_inst * d.n_samples;
   if (b >= bs) return;
-  if (!jampr_step_active(s.ctl, step_no)) return;
-  const int ins = b / d.n_samples, K = d.n_slots;
-  const int slot = action[2 * b], node = action[2 * b + 1];
+  // control words and the rollout's action in one round trip
+  const int c_done = s.ctl[JAMPR_CTL_DONE_STEP], c_hold = s.ctl[JAMPR_CTL_HOLD], c_fin = s.ctl[JAMPR_CTL_FINAL_STEP],
+            c_ld = s.ctl[JAMPR_CTL_LOCAL_DONE];
+  const int2 act = *reinterpret_cast<const int2*>(action + 2 * (size_t)b);
   const bool before = s.allvis[b] != 0;
-  s.cost[b] = env_apply_move(d, p, s, b, ins, slot, node);
-  if (!before && s.nvis[b] == d.n_nodes - 1) {
+  if (!jampr_step_active_w(c_done, c_hold, c_fin, c_ld, step_no)) return;
+  const int ins = b / d.n_samples, K = d.n_slots;
+  const int slot = act.x, node = act.y;
+  int nvis_now;
+  s.cost[b] = env_apply_move(d, p, s, b, ins, slot, node, &nvis_now);
+  if (!before && nvis_now == d.n_nodes - 1) {
     s.allvis[b] = 1;
     atomicAdd(s.ctl + JAMPR_CTL_N_ALLVIS, 1);
   }
@@ -206,19 +314,24 @@ __global__ void __launch_bounds__(ENV_THREADS) env_move_kernel(jampr_dims_t d, j
 }
 
 // ---- step part 2: termination (needs the batch-wide completed count), totals, next observation
-__global__ void __launch_bounds__(ENV_THREADS) env_observe_kernel(jampr_dims_t d, jampr_instances_t p,
+__global__ void __launch_bounds__(ENV_THREADS, 8) env_observe_kernel(jampr_dims_t d, jampr_instances_t p,
                                                                   jampr_state_t s, int step_no) {
   extern __shared__ int16_t sdep[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * ENV_WARPS + warp;
   const int bs = d.n_inst * d.n_samples;
   if (b >= bs) return;
-  if (!jampr_step_active(s.ctl, step_no)) return;
   const int ins = b / d.n_samples, K = d.n_slots, N = d.n_nodes;
-  const bool local_done = (s.ctl[JAMPR_CTL_N_ALLVIS] == bs) || (step_no >= N + d.k_max + 1);
+  // link 1: control words, running totals and the rollout's slot state in one round trip
+  const int c_done = s.ctl[JAMPR_CTL_DONE_STEP], c_hold = s.ctl[JAMPR_CTL_HOLD], c_fin = s.ctl[JAMPR_CTL_FINAL_STEP],
+            c_ld = s.ctl[JAMPR_CTL_LOCAL_DONE], c_all = s.ctl[JAMPR_CTL_N_ALLVIS];
+  const float total0 = s.total[b], cost0 = s.cost[b];
+  const ObsPre o = env_obs_prefetch(d, p, s, b, ins, lane);
+  if (!jampr_step_active_w(c_done, c_hold, c_fin, c_ld, step_no)) return;
+  const bool local_done = (c_all == bs) || (step_no >= N + d.k_max + 1);
   bool done = local_done;
-  if (s.ctl[JAMPR_CTL_HOLD] != 0) {
-    const int fin = s.ctl[JAMPR_CTL_FINAL_STEP];
+  if (c_hold != 0) {
+    const int fin = c_fin;
     if (fin < 0) {
       // sharded run, union finishing step not known yet: park here without finalising or observing
       if (local_done) {
@@ -260,8 +373,8 @@ __global__ void __launch_bounds__(ENV_THREADS) env_observe_kernel(jampr_dims_t d
     }
     return;
   }
-  if (lane == 0) s.total[b] = __fadd_rn(s.total[b], s.cost[b]);
-  env_observe(d, p, s, b, ins, lane, sdep + warp * d.k_nbh);
+  if (lane == 0) s.total[b] = __fadd_rn(total0, cost0);
+  env_obs_run(d, p, s, b, ins, lane, sdep + warp * d.k_nbh, o);
 }
 
 // ---- import_sol tail: derive visited / links / counters from the tour buffers
