@@ -63,26 +63,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
 
-// GELU(erf) on two values with the packed fp32 pipe (FFMA2 / FMUL2): erf to 1.5e-7 absolute
-// (Abramowitz-Stegun 7.1.26), well inside the 16-bit operand noise of this path.
+// GELU(erf) on two values with the packed fp32 pipe and ONE special-function op per value.
+//   gelu(x) = x Phi(x) = relu(x) - |x| Phi(-|x|),   Phi(-u) = 2^q(u),  q = log2(erfc(u / sqrt 2) / 2)
+// q is smooth (no pole, ~ -0.72 u^2 for large u), so a degree-5 polynomial fitted for minimax absolute error of
+// Phi on [0, 6.5] (weights = Phi itself; tools/fit_gelu.py) reaches 2.9e-7 in Phi and 1.3e-6 in gelu — the error
+// level of ex2.approx itself and 200x below the 16-bit operand rounding of this path.  The leading coefficient is
+// negative: beyond the fitted range q keeps falling and 2^q underflows to 0 (gelu -> relu), no clamp needed.
+// The previous Abramowitz-Stegun 7.1.26 form needed rcp + ex2 per value and made the layer epilogue bound by the
+// special-function pipe (16 lanes per SM on sm_100a): 2 x 98k MUFU per rollout-step.
 __device__ __forceinline__ float2 gelu2(float2 x) {
-  float2 ax = __fmul2_rn(x, f2(0.70710678118654752f));
-  ax.x = fabsf(ax.x);
-  ax.y = fabsf(ax.y);
-  const float2 dn = __ffma2_rn(ax, f2(0.3275911f), f2(1.0f));
-  const float2 t = make_float2(rcp_approx(dn.x), rcp_approx(dn.y));
-  float2 p = __ffma2_rn(t, f2(-1.061405429f), f2(1.453152027f));      // coefficients negated: p = -poly
-  p = __ffma2_rn(t, p, f2(-1.421413741f));
-  p = __ffma2_rn(t, p, f2(0.284496736f));
-  p = __ffma2_rn(t, p, f2(-0.254829592f));
-  p = __fmul2_rn(p, t);
-  float2 z = __fmul2_rn(ax, ax);
-  z = __fmul2_rn(z, f2(-1.4426950408889634f));
-  const float2 e = make_float2(ex2_approx(z.x), ex2_approx(z.y));
-  const float2 ea = __ffma2_rn(p, e, f2(1.0f));                        // erf(|x| / sqrt 2)
-  const float2 hx = __fmul2_rn(x, f2(0.5f));
-  const float2 sg = make_float2(copysignf(ea.x, x.x), copysignf(ea.y, x.y));
-  return __ffma2_rn(sg, hx, hx);
+  // polynomial in nu = -|x|: odd coefficients carry the sign
+  const float2 nu = make_float2(-fabsf(x.x), -fabsf(x.y));
+  float2 q = __ffma2_rn(nu, f2(0.0005188681534491479f), f2(0.007387245539575815f));
+  q = __ffma2_rn(nu, q, f2(0.05253808572888374f));
+  q = __ffma2_rn(nu, q, f2(-0.45927664637565613f));
+  q = __ffma2_rn(nu, q, f2(1.1510831117630005f));
+  q = __ffma2_rn(nu, q, f2(-1.0000008344650269f));
+  const float2 h = make_float2(ex2_approx(q.x), ex2_approx(q.y));      // Phi(-|x|)
+  return __ffma2_rn(nu, h, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
