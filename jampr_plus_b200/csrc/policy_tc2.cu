@@ -637,10 +637,11 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 sa = cur[2 * i], sb = cur[2 * i + 1], ba = __ldg(bo + 2 * i), bb = __ldg(bo + 2 * i + 1);
-          const float4 va = make_float4(__uint_as_float(acc[8 * i]) + ba.x + sa.x, __uint_as_float(acc[8 * i + 1]) + ba.y + sa.y,
-                                        __uint_as_float(acc[8 * i + 2]) + ba.z + sa.z, __uint_as_float(acc[8 * i + 3]) + ba.w + sa.w);
-          const float4 vb = make_float4(__uint_as_float(acc[8 * i + 4]) + bb.x + sb.x, __uint_as_float(acc[8 * i + 5]) + bb.y + sb.y,
-                                        __uint_as_float(acc[8 * i + 6]) + bb.z + sb.z, __uint_as_float(acc[8 * i + 7]) + bb.w + sb.w);
+          const float2 v0 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(acc[8 * i]), __uint_as_float(acc[8 * i + 1])), make_float2(ba.x, ba.y)), make_float2(sa.x, sa.y));
+          const float2 v1 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(acc[8 * i + 2]), __uint_as_float(acc[8 * i + 3])), make_float2(ba.z, ba.w)), make_float2(sa.z, sa.w));
+          const float2 v2 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])), make_float2(bb.x, bb.y)), make_float2(sb.x, sb.y));
+          const float2 v3 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])), make_float2(bb.z, bb.w)), make_float2(sb.z, sb.w));
+          const float4 va = make_float4(v0.x, v0.y, v1.x, v1.y), vb = make_float4(v2.x, v2.y, v3.x, v3.y);
           *reinterpret_cast<uint4*>(dst + i * 16) =
               make_uint4(as_u32(Elem<T>::from2(va.x, va.y)), as_u32(Elem<T>::from2(va.z, va.w)),
                          as_u32(Elem<T>::from2(vb.x, vb.y)), as_u32(Elem<T>::from2(vb.z, vb.w)));
@@ -699,12 +700,15 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   // (a) column mean / max of node_emb over the nodes (policy.py:179-181): thread = column pair x row parity
   {
     const int c2 = tid & 127, half = tid >> 7;
-    float2 sm = make_float2(0.0f, 0.0f), mx = make_float2(-INFINITY, -INFINITY);
-    for (int n = half; n < N; n += 2) {
-      const float2 v = Elem<T>::to2(*reinterpret_cast<const T2*>(s_ne16 + (size_t)n * NE16_STRIDE + c2 * 4));
-      sm.x += v.x; sm.y += v.y;
-      mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y);
+    // the maximum commutes with the 16-bit rounding: it is taken on the packed operand type, the sum in fp32
+    T2 mxh = *reinterpret_cast<const T2*>(s_ne16 + (size_t)half * NE16_STRIDE + c2 * 4);
+    float2 sm = Elem<T>::to2(mxh);
+    for (int n = half + 2; n < N; n += 2) {
+      const T2 raw = *reinterpret_cast<const T2*>(s_ne16 + (size_t)n * NE16_STRIDE + c2 * 4);
+      mxh = __hmax2(mxh, raw);
+      sm = __fadd2_rn(sm, Elem<T>::to2(raw));
     }
+    const float2 mx = Elem<T>::to2(mxh);
     *reinterpret_cast<float2*>(s_stat + half * 256 + 2 * c2) = sm;
     *reinterpret_cast<float2*>(s_stat + (2 + half) * 256 + 2 * c2) = mx;
   }
@@ -761,18 +765,18 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     const int nc = s_cnt[2];
     for (int i = warp; i < nc + K; i += P2_WARPS) {
       const int n = i < nc ? (int)s_cand[i] : N + (i - nc);
-      float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+      float2 e0 = make_float2(0.0f, 0.0f), e1 = e0, e2 = e0, e3 = e0;      // even / odd columns accumulate separately
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float2 v;
         if (n < N) v = Elem<T>::to2(*reinterpret_cast<const T2*>(s_ne16 + (size_t)n * NE16_STRIDE + (lane + 32 * i) * 4));
         else v = *reinterpret_cast<const float2*>(s_te + (n - N) * 256 + 2 * (lane + 32 * i));
-        d0 = fmaf(v.x, qv[0][i].x, fmaf(v.y, qv[0][i].y, d0));
-        d1 = fmaf(v.x, qv[1][i].x, fmaf(v.y, qv[1][i].y, d1));
-        d2 = fmaf(v.x, qv[2][i].x, fmaf(v.y, qv[2][i].y, d2));
-        d3 = fmaf(v.x, qv[3][i].x, fmaf(v.y, qv[3][i].y, d3));
+        e0 = __ffma2_rn(v, qv[0][i], e0);
+        e1 = __ffma2_rn(v, qv[1][i], e1);
+        e2 = __ffma2_rn(v, qv[2][i], e2);
+        e3 = __ffma2_rn(v, qv[3][i], e3);
       }
-      const float z = warp_sum4(d0, d1, d2, d3, lane);
+      const float z = warp_sum4(e0.x + e0.y, e1.x + e1.y, e2.x + e2.y, e3.x + e3.y, lane);
       if ((lane & 7) == 0) {
         const int h = ((lane >> 4) << 1) | ((lane >> 3) & 1);
         if (n < N) reinterpret_cast<float*>(s_sn4)[n * 4 + h] = z;
@@ -884,15 +888,15 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     const int nc = s_cnt[2];
     for (int i = warp; i < nc + K; i += P2_WARPS) {
       const int n = i < nc ? (int)s_cand[i] : N + (i - nc);
-      float dd = 0.0f;
+      float2 d2 = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float2 v;
         if (n < N) v = Elem<T>::to2(*reinterpret_cast<const T2*>(s_ne16 + (size_t)n * NE16_STRIDE + (lane + 32 * i) * 4));
         else v = *reinterpret_cast<const float2*>(s_te + (n - N) * 256 + 2 * (lane + 32 * i));
-        dd = fmaf(v.x, lv[i].x, fmaf(v.y, lv[i].y, dd));
+        d2 = __ffma2_rn(v, lv[i], d2);
       }
-      dd = warp_sum(dd);
+      float dd = warp_sum(d2.x + d2.y);
       if (lane == 0) {
         if (n < N) s_ln[n] = dd;
         else s_lt[n - N] = dd;
