@@ -1,17 +1,14 @@
-// Fused environment kernels: transition + tour buffers + vehicle hand-over (env_move), termination +
-// candidate sets + feasibility masks (env_observe).  One warp per rollout; per-rollout state is SoA in
-// HBM (include/jampr_b200.h), static tables are per instance.  HBM-bound integer/compare work: ~0.3 KB of
-// state read+written and <= K*k candidate rows touched per rollout and step.
+// Fused environment kernels: transition + tour buffers + vehicle hand-over (env_move, one thread per rollout),
+// termination + candidate sets + feasibility masks (env_observe, one warp per rollout).  Per-rollout state is SoA
+// in HBM (include/jampr_b200.h), static tables are per instance (L2 resident across the samples of an instance).
+// Integer/compare work on ~1.5 KB of algorithmic bytes per rollout and step; each kernel is organised as a short
+// chain of dependent round trips with all independent loads of a link issued together.
 // Reference semantics: env.py:203-311 (step), :1075-1131 (_update), :848-907 (get_node_nbh),
 // :932-1022 (_get_nbh_and_mask), :1133-1170 (_return_all), :1221-1297 (_reset_pomo).
 #include "common.cuh"
 
 #define ENV_WARPS 4
 #define ENV_THREADS (ENV_WARPS * 32)
-
-struct Roll {
-  int b, ins, lane;
-};
 
 // ---- one transition, executed by one thread (A.4 steps 1-5). Returns the step cost.
 // Every load is issued before the first store: the kernel is a chain of dependent HBM round trips, and the only
