@@ -25,6 +25,41 @@ from .formats import RPInstance, RPObs
 
 __all__ = ["RPEnv", "DeviceState"]
 
+# Debug aid (compute-sanitizer is not available on every pool): with GUARD_BYTES > 0 every device buffer the kernels
+# write is carved out of a larger allocation with GUARD_BYTES of 0xA5 on both sides; ``check_guards`` verifies the
+# pattern.  Set through JAMPR_DEBUG_GUARD=<bytes> or by the tests (tests/test_gpu_guards.py).
+import os as _os
+
+GUARD_BYTES = int(_os.environ.get("JAMPR_DEBUG_GUARD", "0"))
+
+
+class _GuardedAlloc:
+    """Allocator of zero-initialised device tensors, optionally fenced by guard bytes."""
+
+    def __init__(self):
+        self.fenced = []      # (label, raw uint8 tensor, payload bytes, guard bytes)
+
+    def zeros(self, shape, dtype, device, label=""):
+        if GUARD_BYTES <= 0:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        g = (GUARD_BYTES + 255) // 256 * 256           # keeps the payload 256-byte aligned
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        raw = torch.full((n + 2 * g,), 0xA5, dtype=torch.uint8, device=device)
+        self.fenced.append((label, raw, n, g))
+        view = raw[g:g + n]
+        view.zero_()
+        return view.view(dtype).view(shape)
+
+    def check(self):
+        bad = []
+        for label, raw, n, g in self.fenced:
+            if not bool((raw[:g] == 0xA5).all()) or not bool((raw[g + n:] == 0xA5).all()):
+                bad.append(label)
+        if bad:
+            raise RuntimeError(f"guard bytes overwritten around: {bad}")
+        return len(self.fenced)
+
+
 _STATE_SPEC = {
     # name: (dtype, shape as a lambda of dims)
     "visited": (torch.uint8, lambda s: (s.bs, s.N)),
@@ -73,8 +108,9 @@ class DeviceState:
         self.bs, self.N, self.K, self.k, self.K_max, self.L = bs, N, K, k, K_max, L
         self.device = device
         self.t = {}
+        self._alloc = _GuardedAlloc()
         for name, (dt, shp) in _STATE_SPEC.items():
-            self.t[name] = torch.zeros(shp(self), dtype=dt, device=device)
+            self.t[name] = self._alloc.zeros(shp(self), dt, device, name)
         self.want_logp = False
         self._struct = None
 
@@ -84,12 +120,12 @@ class DeviceState:
             if name == "logp" and not (want_logp or self.want_logp):
                 continue
             if name not in self.t:
-                self.t[name] = torch.zeros(shp(self), dtype=dt, device=self.device)
+                self.t[name] = self._alloc.zeros(shp(self), dt, self.device, name)
                 changed = True
         if self.N > 128:
             for name, (dt, shp) in _LARGE_SPEC.items():
                 if name not in self.t:
-                    self.t[name] = torch.zeros(shp(self), dtype=dt, device=self.device)
+                    self.t[name] = self._alloc.zeros(shp(self), dt, self.device, name)
                     changed = True
         self.want_logp = self.want_logp or want_logp
         if changed:
@@ -173,6 +209,15 @@ class RPEnv:
         torch.manual_seed(seed)
         self._gen.manual_seed(seed)
         return [seed]
+
+    def check_guards(self) -> int:
+        """Debug aid: verify the guard bytes around every kernel-written buffer (GUARD_BYTES > 0); returns the
+        number of fenced buffers, raises RuntimeError naming the buffers whose fences were overwritten."""
+        n = 0
+        for a in (getattr(self, "_table_alloc", None), getattr(getattr(self, "state", None), "_alloc", None)):
+            if a is not None:
+                n += a.check()
+        return n
 
     def clear_cache(self):
         self.bs = None
@@ -261,21 +306,22 @@ class RPEnv:
         N, k = gs, self.k_nbh_size
         shape_key = (I, N, k)
         if getattr(self, "_table_key", None) != shape_key:
-            self._dist_mat = torch.empty(I, N, N, dtype=torch.float32, device=dev)
-            self.time_to_depot = torch.empty(I, N, dtype=torch.float32, device=dev)
-            self._knn = torch.empty(I, N, k, dtype=torch.int16, device=dev)
-            self._knn_w = torch.empty(I, N, k, dtype=torch.float32, device=dev)
-            self.ordered_idx = torch.empty(I, N, dtype=torch.int16, device=dev)
-            self._inst_status = torch.zeros(I, dtype=torch.int32, device=dev)
-            self._static_emb = torch.empty(I, N, 256, dtype=torch.float32, device=dev)
-            self._h0 = torch.empty(I, N, 128, dtype=torch.float32, device=dev)
+            ta = self._table_alloc = _GuardedAlloc()
+            self._dist_mat = ta.zeros((I, N, N), torch.float32, dev, "dist")
+            self.time_to_depot = ta.zeros((I, N), torch.float32, dev, "ttd")
+            self._knn = ta.zeros((I, N, k), torch.int16, dev, "knn")
+            self._knn_w = ta.zeros((I, N, k), torch.float32, dev, "knn_w")
+            self.ordered_idx = ta.zeros((I, N), torch.int16, dev, "order")
+            self._inst_status = ta.zeros((I,), torch.int32, dev, "inst_status")
+            self._static_emb = ta.zeros((I, N, 256), torch.float32, dev, "static_emb")
+            self._h0 = ta.zeros((I, N, 128), torch.float32, dev, "h0")
             # packed edge tables of the tensor-core policy step (filled by jampr_node_encoder)
-            self._tc_tab = torch.zeros(I, N, (k + 3) // 4 * 4, dtype=torch.int32, device=dev)
-            self._tc_dtab = torch.zeros(I, (N + 7) // 8 * 8, dtype=torch.int32, device=dev)
+            self._tc_tab = ta.zeros((I, N, (k + 3) // 4 * 4), torch.int32, dev, "tc_tab")
+            self._tc_dtab = ta.zeros((I, (N + 7) // 8 * 8), torch.int32, dev, "tc_dtab")
             # scratch of the tensor-core node encoder (csrc/gnn_large.cu): 16-bit ping-pong embedding + fp32 skip
             npad = (N + 127) // 128 * 128
-            self._lg_h16 = torch.zeros(2, I, npad, 128, dtype=torch.int16, device=dev)
-            self._lg_skip = torch.zeros(I, npad, 128, dtype=torch.float32, device=dev)
+            self._lg_h16 = ta.zeros((2, I, npad, 128), torch.int16, dev, "lg_h16")
+            self._lg_skip = ta.zeros((I, npad, 128), torch.float32, dev, "lg_skip")
             self._table_key = shape_key
         self.bs = I * self._num_samples
         self._dims = _cabi.Dims(I, self._num_samples, N, K, k, self.max_vehicle_number, min(64, N),

@@ -1,0 +1,97 @@
+"""Out-of-bounds writes: every buffer the kernels write is fenced with guard bytes (routing/env.py: GUARD_BYTES) and
+the fences are checked after whole episodes on each kernel family — fp32 path, two-CTA and one-CTA tensor-core
+tilings, the layer-wise large-graph path, and the import_sol / repair path.  (compute-sanitizer is not available on
+the GPU pool, so this is the memory check the suite carries.)"""
+import warnings
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def guards(monkeypatch):
+    import jampr_plus_b200.routing.env as envmod
+    monkeypatch.setattr(envmod, "GUARD_BYTES", 4096)
+    return envmod
+
+
+def _episode(guards, n_customers, K, k_frac, P, precision, n_inst=5, upd=1):
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.driver import rollout
+    from jampr_plus_b200.synth import sample_instances
+    from jampr_plus_b200.weights import random_state_dict
+    env = RPEnv(max_concurrent_vehicles=K, k_nbh_frac=k_frac, pomo=True, num_samples=P, inference=True, device="cuda",
+                tour_graph_update_step=upd)
+    env.seed(2)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision)
+    pol.load_state_dict(random_state_dict(3))
+    pol.eval()
+    env.load_data(sample_instances(n_inst, graph_size=n_customers, seed=1))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        env.reset()
+        total, _ = rollout(pol, env)
+        assert torch.isfinite(total).all()
+    torch.cuda.synchronize()
+    assert env.check_guards() >= 20
+    return env, pol
+
+
+@pytest.mark.parametrize("n_customers,K,k_frac,P,precision,upd", [
+    (100, 3, 0.25, 16, "fp16", 1),     # headline shape, two-CTA tiling
+    (100, 3, 0.25, 4, "bf16", 2),      # cached tour-graph embedding (h_fin / ne stores)
+    (100, 3, 0.25, 4, "fp32", 1),      # CUDA-core anchor
+    (127, 4, 0.2, 2, "fp16", 1),       # full 128-row tile, one-CTA tiling
+    (37, 1, 0.5, 3, "fp16", 1),        # ragged small graph, single vehicle
+    (9, 2, 0.9, 2, "fp16", 1),         # tiny graph, k close to N
+])
+def test_no_write_outside_buffers(guards, n_customers, K, k_frac, P, precision, upd):
+    _episode(guards, n_customers, K, k_frac, P, precision, upd=upd)
+
+
+def test_no_write_outside_buffers_large_graph(guards):
+    # N = 301: three row tiles with a partial last one, layer-wise kernels + fp32 decoder; 40 steps are enough to
+    # run every kernel of the path several times
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.synth import sample_instances
+    from jampr_plus_b200.weights import random_state_dict
+    env = RPEnv(max_concurrent_vehicles=3, k_nbh_frac=0.1, pomo=True, num_samples=2, inference=True, device="cuda",
+                tour_graph_update_step=2)
+    env.seed(2)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp16")
+    pol.load_state_dict(random_state_dict(3))
+    pol.eval()
+    env.load_data(sample_instances(2, graph_size=300, seed=1))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        obs = env.reset()
+        for _ in range(40):
+            action, _, _ = pol(obs)
+            obs, _, done, _ = env.step(action)
+            if done:
+                break
+    torch.cuda.synchronize()
+    assert env.check_guards() >= 20
+
+
+def test_no_write_outside_buffers_lns(guards):
+    """construct -> export -> destroy -> import_sol -> repair rollouts (the LNS inner loop, graph replay included)."""
+    import os
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.lns import LNS, read_solomon
+    from jampr_plus_b200.weights import random_state_dict
+    data = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+    inst = read_solomon(os.path.join(data, "c103.txt"))
+    env = RPEnv(max_concurrent_vehicles=3, k_nbh_frac=0.25, pomo=True, num_samples=20, inference=True,
+                tour_graph_update_step=2, device="cuda")
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp16")
+    pol.load_state_dict(random_state_dict(0))
+    pol.eval()
+    lns = LNS(inst, pol, env, seed=7)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        lns.search(num_steps=4)
+    torch.cuda.synchronize()
+    assert env.check_guards() >= 20
