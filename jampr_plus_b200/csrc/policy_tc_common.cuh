@@ -148,8 +148,10 @@ __device__ __forceinline__ void agg_edge2(uint32_t e, uint32_t hb, uint32_t cA, 
                                           bool first) {
   using T2 = typename Elem<T>::T2;
   const T2 w2 = from_u32<T2>(__byte_perm(e, e, 0x3232));
-  const uint32_t ro = e & 0xffffu;
-  const uint4 va = lds128(hb + (ro ^ cA)), vb = lds128(hb + (ro ^ cB));
+  // cB == cA ^ 0x40 at every call site and hb is 1 KB aligned: the second address is one XOR away from the first
+  (void)cB;
+  const uint32_t aA = hb + ((e & 0xffffu) ^ cA);
+  const uint4 va = lds128(aA), vb = lds128(aA ^ 0x40u);
   const T2 p0 = __hmul2(from_u32<T2>(va.x), w2), p1 = __hmul2(from_u32<T2>(va.y), w2);
   const T2 p2 = __hmul2(from_u32<T2>(va.z), w2), p3 = __hmul2(from_u32<T2>(va.w), w2);
   const T2 p4 = __hmul2(from_u32<T2>(vb.x), w2), p5 = __hmul2(from_u32<T2>(vb.y), w2);
