@@ -131,7 +131,8 @@ __device__ __forceinline__ void layer_epilogue2(uint32_t tmem, uint8_t* sA, uint
   const float2 v0 = s_red[r], v1 = s_red[128 + r];
   const float mean = (v0.x + v1.x) * (1.0f / 128.0f);
   const float var = fmaxf(fmaf(-mean, mean, (v0.y + v1.y) * (1.0f / 128.0f)), 0.0f);
-  const float2 rstd2 = f2(rsqrtf(var + 1e-5f)), nmean2 = f2(-mean);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float2 rstd2 = f2(rstd), shift2 = f2(-mean * rstd);      // (y - mean) rstd = y rstd + shift: one FFMA2
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
     const int col0 = ch * 64 + c * 32;
@@ -142,10 +143,10 @@ __device__ __forceinline__ void layer_epilogue2(uint32_t tmem, uint8_t* sA, uint
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 g4 = lds_f32x4(pb + 512 + i * 16), e4 = lds_f32x4(pb + 1024 + i * 16);
-      const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1])), nmean2);
-      const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), nmean2);
-      const float2 o0 = __ffma2_rn(d0, __fmul2_rn(make_float2(g4.x, g4.y), rstd2), make_float2(e4.x, e4.y));
-      const float2 o1 = __ffma2_rn(d1, __fmul2_rn(make_float2(g4.z, g4.w), rstd2), make_float2(e4.z, e4.w));
+      const float2 d0 = __ffma2_rn(make_float2(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1])), rstd2, shift2);
+      const float2 d1 = __ffma2_rn(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), rstd2, shift2);
+      const float2 o0 = __ffma2_rn(d0, make_float2(g4.x, g4.y), make_float2(e4.x, e4.y));
+      const float2 o1 = __ffma2_rn(d1, make_float2(g4.z, g4.w), make_float2(e4.z, e4.w));
       acc[4 * i] = __float_as_uint(o0.x); acc[4 * i + 1] = __float_as_uint(o0.y);
       acc[4 * i + 2] = __float_as_uint(o1.x); acc[4 * i + 3] = __float_as_uint(o1.y);
     }
