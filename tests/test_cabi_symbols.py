@@ -109,3 +109,30 @@ def test_policy_refuses_cpu_and_checks_schema():
         pol.load_state_dict(bad)
     with pytest.raises(NotImplementedError):
         Policy(RPEnv.OBSERVATION_SPACE, device="cpu", embedding_dim=128)
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/jampr_b200.h is the drop-in boundary: it must compile as C99 and as C++ without CUDA or torch headers,
+    and a C translation unit that takes the address of every entry point must link against the library."""
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "jampr_b200.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                   check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    names = sorted(set(re.findall(r"\b(jampr_[a-z0-9_]+)\s*\(", open(hdr).read())))
+    assert len(names) >= 15
+    src = tmp_path / "link.c"
+    src.write_text('#include "jampr_b200.h"\n#include <stdio.h>\nint main(void) {\n  void* p[] = {'
+                   + ", ".join(f"(void*){n}" for n in names)
+                   + '};\n  printf("%d %d\\n", (int)(sizeof(p) / sizeof(p[0])), jampr_abi_version());\n  return 0;\n}\n')
+    lib_dir = os.path.join(root, "jampr_plus_b200", "lib")
+    exe = tmp_path / "link"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-ljampr_b200", f"-Wl,-rpath,{lib_dir}", "-Wno-pedantic"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == len(names) and int(out[1]) == 3
