@@ -596,13 +596,12 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         umma_commit(bar_acc);
       }
       if (proj) break;
+      mbar_wait(bar_acc, ph);                         // every thread waits for the accumulator itself (no block barrier hop)
       if (tid == 0) {
-        mbar_wait(bar_acc, ph);                       // one waiter; everybody else parks at the block barrier
-        const int nl = l + 1;                         // next layer's first pair
+        const int nl = l + 1;                         // next layer's first pair: both stages are free again
         load_w2<T>(sW, 0, a.w16, nl * 4 + (nl == 6 ? 0 : 2), full);
         load_w2<T>(sW, 1, a.w16, nl * 4 + (nl == 6 ? 1 : 3), full);
       }
-      __syncthreads();
       tc_fence_after();
       if (!(ABL(2)))
         layer_epilogue2<T>(tmem, sA, ts, s_red, par_saddr, N,
