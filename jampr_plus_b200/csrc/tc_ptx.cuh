@@ -36,9 +36,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Blocking wait: one asm block (address computed once, two instructions per retry) and a suspend-time hint so the
+// hardware parks the thread instead of spinning through issue slots that the co-resident CTA could use.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "JAMPR_MBAR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra JAMPR_MBAR_DONE;\n\t"
+      "bra JAMPR_MBAR_WAIT;\n\t"
+      "JAMPR_MBAR_DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- proxies / fences
