@@ -105,8 +105,10 @@ __device__ __forceinline__ ObsPre env_obs_prefetch(const jampr_dims_t& d, const 
   return o;
 }
 
-__device__ void env_obs_run(const jampr_dims_t& d, const jampr_instances_t& p, const jampr_state_t& s,
-                            int b, int ins, int lane, int16_t* dep /* smem [k] */, const ObsPre& o) {
+// G = slots handled together (compile-time width of the register arrays): min(K, 4)
+template <int G>
+__device__ __forceinline__ void env_obs_run_g(const jampr_dims_t& d, const jampr_instances_t& p, const jampr_state_t& s,
+                                              int b, int ins, int lane, int16_t* dep /* smem [k] */, const ObsPre& o) {
   const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh;
   // per-warp base pointers once, 32-bit offsets inside the rows
   const uint8_t* vis = s.visited + (size_t)b * N;
@@ -119,9 +121,9 @@ __device__ void env_obs_run(const jampr_dims_t& d, const jampr_instances_t& p, c
   const bool allvis = o.nvis == N - 1;
   const bool any_depot = __any_sync(0xffffffffu, lane < K && o.cur == 0);
   // link 2
-  int cur0[4], kn0[4];
+  int cur0[G], kn0[G];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < G; ++i) {
     cur0[i] = __shfl_sync(0xffffffffu, o.cur, min(i, K - 1));
     kn0[i] = 0;
     if (lane < k && i < K && cur0[i] != 0) kn0[i] = knn[cur0[i] * k + lane];
@@ -177,19 +179,19 @@ __device__ void env_obs_run(const jampr_dims_t& d, const jampr_instances_t& p, c
   for (int j0 = 0; j0 < k; j0 += 32) {
     const int j = j0 + lane;
     const bool valid = j < k;
-    for (int tb = 0; tb < K; tb += 4) {
+    for (int tb = 0; tb < K; tb += G) {
       const bool first = (j0 | tb) == 0;
-      int cur[4], n[4];
-      float cap[4], tm[4];
+      int cur[G], n[G];
+      float cap[G], tm[G];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < G; ++i) {
         const int t = min(tb + i, K - 1);
         cur[i] = __shfl_sync(0xffffffffu, o.cur, t);
         cap[i] = __shfl_sync(0xffffffffu, o.cap, t);
         tm[i] = __shfl_sync(0xffffffffu, o.tm, t);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < G; ++i) {
         n[i] = 0;
         if (valid && tb + i < K) {
           if (cur[i] == 0) n[i] = dep[j];
@@ -197,17 +199,17 @@ __device__ void env_obs_run(const jampr_dims_t& d, const jampr_instances_t& p, c
         }
       }
       // link 3
-      uint8_t vs[4];
-      float dm[4], dr[4], tc[4];
+      uint8_t vs[G];
+      float dm[G], dr[G], tc[G];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < G; ++i) {
         vs[i] = vis[n[i]];
         dm[i] = demand_i[n[i]];
         dr[i] = dist_i[cur[i] * N + n[i]];
         tc[i] = tw_i[n[i] * 2 + 1];
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < G; ++i) {
         if (valid && tb + i < K) {
           const int e = (tb + i) * k + j;
           bool m = vs[i] != 0;
@@ -224,6 +226,16 @@ __device__ void env_obs_run(const jampr_dims_t& d, const jampr_instances_t& p, c
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) open_bits |= __shfl_xor_sync(0xffffffffu, open_bits, sh);
   if (lane == 0 && open_bits != ((1u << K) - 1u)) s.status[b] |= JAMPR_ST_NO_FEASIBLE;
+}
+
+__device__ void env_obs_run(const jampr_dims_t& d, const jampr_instances_t& p, const jampr_state_t& s,
+                            int b, int ins, int lane, int16_t* dep /* smem [k] */, const ObsPre& o) {
+  switch (d.n_slots) {
+    case 1: env_obs_run_g<1>(d, p, s, b, ins, lane, dep, o); break;
+    case 2: env_obs_run_g<2>(d, p, s, b, ins, lane, dep, o); break;
+    case 3: env_obs_run_g<3>(d, p, s, b, ins, lane, dep, o); break;
+    default: env_obs_run_g<4>(d, p, s, b, ins, lane, dep, o); break;
+  }
 }
 
 __device__ __forceinline__ void env_observe(const jampr_dims_t& d, const jampr_instances_t& p, const jampr_state_t& s,
