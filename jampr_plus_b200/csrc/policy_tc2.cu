@@ -21,6 +21,15 @@
 #define ABL(bit) false
 #endif
 
+// per-phase time line of sampled CTAs (tools/timeline.py): build with `make EXTRA=-DJAMPR_TIMELINE`
+#ifdef JAMPR_TIMELINE
+#define TL_N 40
+__device__ uint32_t g_timeline[1024][TL_N];
+#define TL(k) do { if (threadIdx.x == 0) s_tl[k] = (uint32_t)clock64(); } while (0)
+#else
+#define TL(k) do { } while (0)
+#endif
+
 #define P2_THREADS 256
 #define P2_WARPS (P2_THREADS / 32)
 #define P2_GROUPS ((P2_THREADS - 32) / 8)    // customer rows aggregated concurrently (warps 1..7, 8 threads per row)
@@ -332,6 +341,12 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     }
     return;
   }
+#ifdef JAMPR_TIMELINE
+  __shared__ uint32_t s_tl[TL_N];
+  if (tid < TL_N) s_tl[tid] = 0u;
+  __syncthreads();
+#endif
+  TL(0);
   const float* __restrict__ w = a.w;
   const T* __restrict__ w16 = reinterpret_cast<const T*>(a.w16);
   const bool fresh = a.graph_fresh != 0;
@@ -464,6 +479,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   tc_fence_before();
   __syncthreads();
+  TL(1);
   tc_fence_after();
 
   const int q4 = warp & 3, ch = warp >> 2, r = q4 * 32 + lane;      // epilogue role: row r, columns 64ch..64ch+63
@@ -524,6 +540,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+  TL(2);
     tc_fence_after();
 
     const uint32_t tab_saddr = smem_u32(s_tab), dtab_saddr = smem_u32(s_dtab), par_saddr = smem_u32(s_par);
@@ -559,6 +576,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         fence_proxy_async();
       }
       __syncthreads();
+      TL(3 + 3 * l);
       if (proj) {
         // per-tour mean of h over buffer positions 0..idx (one depot entry included, tour_encoder.py:236-243);
         // overlaps the projection MMAs.  The edge tables are dead: s_mean overlays them (hence the barrier above).
@@ -597,6 +615,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       }
       if (proj) break;
       mbar_wait(bar_acc, ph);                         // every thread waits for the accumulator itself (no block barrier hop)
+      TL(4 + 3 * l);
       if (tid == 0) {
         const int nl = l + 1;                         // next layer's first pair: both stages are free again
         load_w2<T>(sW, 0, a.w16, nl * 4 + (nl == 6 ? 0 : 2), full);
@@ -610,6 +629,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
+      TL(5 + 3 * l);
     }
     // ---- node embedding rows: ne = acc + b + static_emb -> parked 16-bit rows (+ fp32 to HBM when cached).
     // The static_emb rows come from L2: chunk c+1 is in flight while chunk c is combined; chunk 0 is requested
@@ -622,6 +642,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     for (int i = 0; i < 8; ++i) sv1[i] = __ldg(se_row + 8 + i);
     if (tid == 0) mbar_wait(bar_acc, 0u);
     __syncthreads();          // projection complete and per-tour means done: the h tiles may be overwritten
+  TL(21);
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -674,6 +695,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     }
   }
   __syncthreads();
+  TL(22);
   if (fresh && warp == 0) {
     tc_fence_after();
     tmem_dealloc(*tmem_slot, 256);
@@ -734,6 +756,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     s_q[256 + tid] = nmax + mx;
   }
   __syncthreads();
+  TL(23);
   // (c) ctxt = ctxt_proj(query)
   if (mv) matvec2_pipe<T>(w16 + W16_CTXT, 512, smem_u32(s_q), s_part, pre);
   mv_prefetch<T>(w16 + W16_GK, 256, pre);
@@ -745,6 +768,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     s_ctxt[tid] = v;
   }
   __syncthreads();
+  TL(24);
   // (d) qp[h] = W_gk,h^T ctxt_h : K-slice ks (32 rows of set_proj) belongs to head ks / 2
   if (mv) matvec2_pipe<T>(w16 + W16_GK, 256, smem_u32(s_ctxt), s_part, pre);
   mv_prefetch<T>(w16 + W16_GV, 256, pre);            // consumed after the glimpse softmax: fully hidden
@@ -754,6 +778,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     s_qp[h * QP2_STRIDE + c] = s_part[(2 * h) * 256 + c] + s_part[(2 * h + 1) * 256 + c];
   }
   __syncthreads();
+  TL(25);
   // (e) per-node and per-tour glimpse scores qp_h . node_emb[n], qp_h . tour_emb[t]: one warp per row; lane owns the
   // column pairs 2 (lane + 32 i), i < 4, of the four query vectors in registers
   {
@@ -785,6 +810,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     }
   }
   __syncthreads();
+  TL(26);
   // (f) glimpse scores per action, softmax per head
   for (int e = tid; e < 4 * A; e += P2_THREADS) {
     const int h = e / A, aa = e - h * A;
@@ -824,6 +850,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     s_P[h * 8 + t] = acc;
   }
   __syncthreads();
+  TL(27);
   // (g) gbar[h] = sum_a p[h][a] act[a] = sum_t P[h][t] tour_emb[t] + sum_n pn[h][n] node_emb[n]
   {
     const int c2 = tid & 127, half = tid >> 7;
@@ -859,6 +886,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     s_gbar[h * QP2_STRIDE + c] = s_part[h * 256 + c] + s_part[(4 + h) * 256 + c];
   }
   __syncthreads();
+  TL(28);
   // (h) glimpse g[o] = W_gv[o] . gbar[head(o)]
   if (mv) matvec2_pipe<T>(w16 + W16_GV, 256, smem_u32(s_gbar) + (uint32_t)((tid & 31) >> 3) * QP2_STRIDE * 4u, s_part, pre);
   mv_prefetch<T>(w16 + W16_M1, 256, pre);
@@ -870,6 +898,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     s_g[tid] = v;
   }
   __syncthreads();
+  TL(29);
   // (i) lp = W_lk^T out_proj(g) = M1 g
   if (mv) matvec2_pipe<T>(w16 + W16_M1, 256, smem_u32(s_g), s_part, pre);
   __syncthreads();
@@ -880,6 +909,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     s_lp[tid] = v;
   }
   __syncthreads();
+  TL(30);
   // (j) pointer logits: 10 tanh((lp . node_emb[n] + lp . tour_emb[t]) / 16)
   {
     float2 lv[4];
@@ -907,6 +937,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   for (int aa = tid; aa < A; aa += P2_THREADS)
     s_logit[aa] = s_mask[aa] ? -INFINITY : 10.0f * tanhf((s_ln[s_nbh[aa]] + s_lt[aa / k]) * 0.0625f);
   __syncthreads();
+  TL(31);
   // ---- log-softmax + selection (warp 0), same rules as decoder.cu
   if (warp == 0) {
     float mx = -INFINITY;
@@ -970,9 +1001,22 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       st.ll[b] = s_logit[choice];
       st.entropy[b] = ent;
       if (nan) atomicOr(st.status + b, JAMPR_ST_NAN_LOGITS);
+#ifdef JAMPR_TIMELINE
+      s_tl[32] = (uint32_t)clock64();
+      if ((b & 63) == 0 && (b >> 6) < 1024)
+        for (int q = 0; q < TL_N; ++q) g_timeline[b >> 6][q] = s_tl[q];
+#endif
     }
   }
 }
+
+#ifdef JAMPR_TIMELINE
+extern "C" __attribute__((visibility("default"))) int jampr_debug_timeline(uint32_t* host_out) {
+  CUDA_RET(cudaDeviceSynchronize());
+  CUDA_RET(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(g_timeline)));
+  return 0;
+}
+#endif
 
 static size_t p2_smem_bytes(const jampr_dims_t* d) {
   const int N = d->n_nodes, k = d->k_nbh, K = d->n_slots, A = K * k, L = d->plan_len;
