@@ -318,6 +318,8 @@ __host__ __device__ inline uint32_t p2_r2_bytes(int N, int k, int A) {
 }
 // bytes of the region shared by the weight stages (GNN phase) and decoder scratch (decoder phase)
 #define P2_R1_BYTES 32768u
+// accumulator row owned by a thread in the epilogue / h_0 phases: TMEM lane quarter = warp & 3
+__device__ __forceinline__ int q4_row(int tid) { return ((tid >> 5) & 3) * 32 + (tid & 31); }
 
 template <typename T>
 __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const PtArgs a) {
@@ -431,45 +433,93 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     // operand rows >= N are never initialised: the MMA reads them, but they only feed accumulator rows >= N, which
     // nothing reads (rows are independent in every later phase)
   }
-  if (tid < 4) s_cnt[tid] = 0;
-  for (int e = tid; e < K * N; e += P2_THREADS) s_pos[e] = (int8_t)-1;
+  // The per-rollout state comes from HBM (10 GB of it per launch: nothing stays in L2), so the prologue is a chain of
+  // dependent round trips.  It is written as two links: everything addressed by (b, tid) alone is requested first
+  // (registers), then the two dependent gathers (tour rows by st.row, link distances by pred / succ).
+  const int rdx = min(q4_row(tid), N - 1);
+  // ---- link 1
+  int row_of = 0, nb0 = 0, pr = 0, su = 0;
+  uint8_t mk0 = 0;
+  bool vs = false;
+  float ttd_u = 0.0f, f_cur = 0.0f, f_cap = 0.0f, f_time = 0.0f, f_cttd = 0.0f;
+  int f_row = 0;
+  if (tid < K * L) row_of = st.row[(size_t)b * K + tid / L];
+  if (tid < A) {
+    nb0 = st.nbh[(size_t)b * A + tid];
+    mk0 = st.mask[(size_t)b * A + tid];
+  }
+  if (fresh && tid < N) {
+    pr = st.pred[(size_t)b * N + tid];
+    su = st.succ[(size_t)b * N + tid];
+    vs = tid > 0 && st.visited[(size_t)b * N + tid] != 0;
+    ttd_u = p.ttd[(size_t)ins * N + tid];
+  }
   if (tid < K) {
     const size_t bk = (size_t)b * K + tid;
-    const int row = st.row[bk];
-    s_feat[tid * 8 + 0] = (float)st.cur[bk];
-    s_feat[tid * 8 + 1] = st.cap[bk];
-    s_feat[tid * 8 + 2] = st.time[bk];
-    s_feat[tid * 8 + 3] = st.cttd[bk];
-    s_feat[tid * 8 + 4] = (float)(d.k_max - row) / (float)d.k_max;
+    f_row = st.row[bk];
+    f_cur = (float)st.cur[bk];
+    f_cap = st.cap[bk];
+    f_time = st.time[bk];
+    f_cttd = st.cttd[bk];
   }
-  for (int e = tid; e < K * L; e += P2_THREADS) {
-    const int t = e / L, q = e - t * L;
-    s_plan[e] = st.plan[((size_t)b * d.k_max + st.row[(size_t)b * K + t]) * L + q];
+  const int n_tab4 = (N * k4) / 4;
+  const uint4* gt = reinterpret_cast<const uint4*>(p.tc_tab + (size_t)ins * N * k4);
+  uint4 tabv[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    tabv[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (fresh && tid + i * P2_THREADS < n_tab4) tabv[i] = __ldg(gt + tid + i * P2_THREADS);
   }
-  for (int e = tid; e < A; e += P2_THREADS) {
+  // h_0 row chunk 0 (per instance, L2): requested here, used after the prologue barriers
+  float4 h0v[8];
+  if (fresh) {
+    const float4* src = reinterpret_cast<const float4*>(p.h0 + ((size_t)ins * N + rdx) * 128 + (tid >> 7) * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h0v[i] = __ldg(src + i);
+  }
+  if (tid < 4) s_cnt[tid] = 0;
+  for (int e = tid; e < K * N; e += P2_THREADS) s_pos[e] = (int8_t)-1;
+  // ---- link 2
+  const float* dist = p.dist + (size_t)ins * N * N;
+  float d_pr = 0.0f, d_su = 0.0f;
+  if (vs) {
+    d_pr = dist[(size_t)tid * N + pr];
+    d_su = dist[(size_t)tid * N + su];
+  }
+  if (tid < K * L) s_plan[tid] = st.plan[((size_t)b * d.k_max + row_of) * L + (tid - (tid / L) * L)];
+  // ---- park link 1
+  if (tid < A) {
+    s_nbh[tid] = nb0;
+    s_mask[tid] = mk0;
+  }
+  for (int e = tid + P2_THREADS; e < A; e += P2_THREADS) {
     s_nbh[e] = st.nbh[(size_t)b * A + e];
     s_mask[e] = st.mask[(size_t)b * A + e];
   }
+  if (tid < K) {
+    s_feat[tid * 8 + 0] = f_cur;
+    s_feat[tid * 8 + 1] = f_cap;
+    s_feat[tid * 8 + 2] = f_time;
+    s_feat[tid * 8 + 3] = f_cttd;
+    s_feat[tid * 8 + 4] = (float)(d.k_max - f_row) / (float)d.k_max;
+  }
+  if (fresh) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (tid + i * P2_THREADS < n_tab4) reinterpret_cast<uint4*>(s_tab)[tid + i * P2_THREADS] = tabv[i];
+    for (int e = tid + 3 * P2_THREADS; e < n_tab4; e += P2_THREADS) reinterpret_cast<uint4*>(s_tab)[e] = __ldg(gt + e);
+    const uint4* gd = reinterpret_cast<const uint4*>(p.tc_dtab + (size_t)ins * nd);
+    for (int e = tid; e < nd / 4; e += P2_THREADS) reinterpret_cast<uint4*>(s_dtab)[e] = __ldg(gd + e);
+  }
   __syncthreads();
   for (int e = tid; e < A; e += P2_THREADS) s_pos[(e / k) * N + s_nbh[e]] = (int8_t)(e % k);
-  if (fresh) {
-    {
-      const uint4* gt = reinterpret_cast<const uint4*>(p.tc_tab + (size_t)ins * N * k4);
-      for (int e = tid; e < (N * k4) / 4; e += P2_THREADS) reinterpret_cast<uint4*>(s_tab)[e] = __ldg(gt + e);
-      const uint4* gd = reinterpret_cast<const uint4*>(p.tc_dtab + (size_t)ins * nd);
-      for (int e = tid; e < nd / 4; e += P2_THREADS) reinterpret_cast<uint4*>(s_dtab)[e] = __ldg(gd + e);
-    }
-    const float* dist = p.dist + (size_t)ins * N * N;
-    for (int u = tid; u < N; u += P2_THREADS) {
-      const int pr = st.pred[(size_t)b * N + u], su = st.succ[(size_t)b * N + u];
-      const bool vs = u > 0 && st.visited[(size_t)b * N + u] != 0;
-      s_lf[u] = vs ? agg_entry((uint32_t)pr, bits_T<T>(dist[(size_t)u * N + pr])) : 0u;
-      s_lr[u] = vs ? agg_entry((uint32_t)su, bits_T<T>(dist[(size_t)u * N + su])) : 0u;
-      if (vs) {
-        const uint32_t en = agg_entry((uint32_t)u, bits_T<T>(p.ttd[(size_t)ins * N + u]));
-        if (su == 0) s_ef[atomicAdd(&s_cnt[0], 1)] = en;
-        if (pr == 0) s_er[atomicAdd(&s_cnt[1], 1)] = en;
-      }
+  if (fresh && tid < N) {
+    s_lf[tid] = vs ? agg_entry((uint32_t)pr, bits_T<T>(d_pr)) : 0u;
+    s_lr[tid] = vs ? agg_entry((uint32_t)su, bits_T<T>(d_su)) : 0u;
+    if (vs) {
+      const uint32_t en = agg_entry((uint32_t)tid, bits_T<T>(ttd_u));
+      if (su == 0) s_ef[atomicAdd(&s_cnt[0], 1)] = en;
+      if (pr == 0) s_er[atomicAdd(&s_cnt[1], 1)] = en;
     }
   }
   if (tid < K) {
@@ -517,7 +567,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         const float4* src = reinterpret_cast<const float4*>(p.h0 + ((size_t)ins * N + r) * 128 + col0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 v = __ldg(src + i);
+          const float4 v = (c == 0) ? h0v[i] : __ldg(src + i);
           hv[4 * i] = __float_as_uint(v.x); hv[4 * i + 1] = __float_as_uint(v.y);
           hv[4 * i + 2] = __float_as_uint(v.z); hv[4 * i + 3] = __float_as_uint(v.w);
         }
