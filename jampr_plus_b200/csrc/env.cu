@@ -475,7 +475,7 @@ __global__ void true_cost_kernel(jampr_dims_t d, jampr_instances_t p, jampr_stat
 static int check_dims(const jampr_dims_t* d) {
   if (!d || d->n_inst <= 0 || d->n_samples <= 0 || d->n_nodes < 2 || d->n_slots <= 0 ||
       d->n_slots > JAMPR_MAX_SLOTS || d->k_nbh < 2 || d->k_nbh > d->n_nodes || d->k_max < d->n_slots ||
-      d->plan_len <= 0 || d->upd_step == 0)
+      d->plan_len <= 0 || d->upd_step <= 0)
     return JAMPR_E_BADARG;
   return 0;
 }

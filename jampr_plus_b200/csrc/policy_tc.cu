@@ -204,6 +204,32 @@ __device__ __forceinline__ void matvec_partial(const T* __restrict__ W, int K, u
     for (int j = 0; j < OPT; ++j) s_part[(ks * NV + v) * 256 + og * OPT + j] = acc[v][j];
 }
 
+// fp32-weight variant (8 outputs per thread, one input vector) for ctxt_proj and the glimpse keys: their 16-bit rounding
+// dominated the log-probability error of the path (see policy_tc2.cu mvf_prefetch)
+__device__ __forceinline__ void matvec_partial_f32(const float* __restrict__ W, int K, uint32_t x_saddr, float* s_part) {
+  constexpr int NG = 32, NS = PT_THREADS / NG;
+  const int og = threadIdx.x % NG, ks = threadIdx.x / NG;
+  const int kn = K / NS, k0 = ks * kn;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  const float* wp = W + (size_t)k0 * 256 + og * 8;
+  const uint32_t xa = x_saddr + (uint32_t)k0 * 4u;
+#pragma unroll 8
+  for (int c = 0; c < kn; ++c) {
+    const float4 wa = __ldg(reinterpret_cast<const float4*>(wp + (size_t)c * 256));
+    const float4 wb = __ldg(reinterpret_cast<const float4*>(wp + (size_t)c * 256) + 1);
+    const float2 xv = f2(lds_f32(xa + (uint32_t)c * 4u));
+    const float2 a0 = __ffma2_rn(make_float2(wa.x, wa.y), xv, make_float2(acc[0], acc[1]));
+    const float2 a1 = __ffma2_rn(make_float2(wa.z, wa.w), xv, make_float2(acc[2], acc[3]));
+    const float2 a2 = __ffma2_rn(make_float2(wb.x, wb.y), xv, make_float2(acc[4], acc[5]));
+    const float2 a3 = __ffma2_rn(make_float2(wb.z, wb.w), xv, make_float2(acc[6], acc[7]));
+    acc[0] = a0.x; acc[1] = a0.y; acc[2] = a1.x; acc[3] = a1.y; acc[4] = a2.x; acc[5] = a2.y; acc[6] = a3.x; acc[7] = a3.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_part[ks * 256 + og * 8 + j] = acc[j];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtArgs a) {
   using T2 = typename Elem<T>::T2;
@@ -555,7 +581,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   }
   __syncthreads();
   // (c) ctxt = ctxt_proj(query)
-  matvec_partial<T, 8, 1>(w16 + W16_CTXT, 512, smem_u32(s_q), 0, s_part);
+  matvec_partial_f32(w + OFF_CTXT_WT, 512, smem_u32(s_q), s_part);
   __syncthreads();
   if (tid < 256) {
     float v = 0.0f;
@@ -565,7 +591,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
   }
   __syncthreads();
   // (d) qp[h] = W_gk,h^T ctxt_h : K-slice ks (16 rows of set_proj) belongs to head ks / 4
-  matvec_partial<T, 8, 1>(w16 + W16_GK, 256, smem_u32(s_ctxt), 0, s_part);
+  matvec_partial_f32(w + OFF_GK_W, 256, smem_u32(s_ctxt), s_part);
   __syncthreads();
   for (int e = tid; e < 1024; e += PT_THREADS) {
     const int h = e >> 8, c = e & 255;

@@ -113,6 +113,7 @@ class DeviceState:
             self.t[name] = self._alloc.zeros(shp(self), dt, device, name)
         self.want_logp = False
         self._struct = None
+        self.graphs = {}      # captured CUDA graphs of rollouts over these buffers (driver._replay_or_capture)
 
     def ensure_policy_buffers(self, want_logp: bool = False):
         changed = False
@@ -191,6 +192,10 @@ class RPEnv:
             raise NotImplementedError("the CUDA environment computes in fp32 (reference default, env.py:41)")
         self.fp_precision = fp_precision
         assert tour_graph_update_step != 0
+        if tour_graph_update_step < 0:
+            # the reference only asserts != 0 (env.py:118); a negative period has no meaning in `_step % period == 0`
+            # beyond "Python's sign convention", and the fused device loop rejects it: refuse it in one place
+            raise ValueError("tour_graph_update_step must be a positive integer")
         self.tour_graph_update_step = tour_graph_update_step
         # the reference keeps the dense distance matrix only in inference mode (env.py:369-372); the kernels
         # always use it, which yields the same values (same formula, challenge_utils.py:35)

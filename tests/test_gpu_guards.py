@@ -25,7 +25,7 @@ def _episode(guards, n_customers, K, k_frac, P, precision, n_inst=5, upd=1):
     env = RPEnv(max_concurrent_vehicles=K, k_nbh_frac=k_frac, pomo=True, num_samples=P, inference=True, device="cuda",
                 tour_graph_update_step=upd)
     env.seed(2)
-    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision, allow_reduced_accuracy=True)
     pol.load_state_dict(random_state_dict(3))
     pol.eval()
     env.load_data(sample_instances(n_inst, graph_size=n_customers, seed=1))

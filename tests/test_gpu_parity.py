@@ -347,7 +347,7 @@ def test_repair_step_import_sol(precision):
         assert np.array_equal(env.total_cost.cpu().numpy(), g["import_total"])
         assert env._step == int(g["import_step"])
         T = g["trace_action"].shape[0]
-        atol = LOGP_ATOL if precision == "fp32" else 2.5e-2
+        # fp16: the 1e-3-relative bar of tests/test_gpu_tc_policy.py (unit floor)
         for t in range(T):
             assert np.array_equal(obs.nbh.cpu().numpy(), g["trace_nbh"][t]), f"nbh step {t}"
             assert np.array_equal(obs.nbh_mask.cpu().numpy(), g["trace_mask"][t]), f"mask step {t}"
@@ -357,7 +357,8 @@ def test_repair_step_import_sol(precision):
             ref = g["trace_logp"][t]
             fin = np.isfinite(ref)
             assert np.array_equal(np.isfinite(logp), fin), f"support step {t}"
-            assert (np.abs(logp[fin] - ref[fin]) <= atol + LOGP_RTOL * np.abs(ref[fin])).all(), t
+            tol = (LOGP_ATOL + LOGP_RTOL * np.abs(ref[fin])) if precision == "fp32" else 1e-3 * np.maximum(1.0, np.abs(ref[fin]))
+            assert (np.abs(logp[fin] - ref[fin]) <= tol).all(), t
             obs, cost, done, _ = env.step(torch.from_numpy(g["trace_action"][t].astype(np.int64)))
             if not done:
                 assert np.array_equal(cost.cpu().numpy(), g["trace_cost"][t]), f"cost step {t}"

@@ -1,12 +1,17 @@
-"""GPU parity of the tensor-core policy step (csrc/policy_tc.cu: tcgen05 GraphConv layers + fused decoder) against the
-golden traces recorded from the reference and against the fp32 CUDA path, under teacher forcing.
+"""GPU parity of the tensor-core policy step (csrc/policy_tc2.cu / policy_tc.cu: tcgen05 GraphConv layers + fused
+decoder) against the golden traces recorded from the reference, under teacher forcing.
 
-What a 16-bit operand path can and cannot promise (rounding only the *weights* of the reference to
-bf16 already moves log-probabilities by up to 0.16 and flips 0.58 % of decisions on this kind of fixture):
+Bars come from BASELINE.json's north_star, not from what the kernel happens to deliver:
   * environment side (candidate sets, masks, costs, tour buffers): bit-exact, it is the same fp32 code;
-  * log-probabilities: absolute error bounded by LOGP_ATOL[precision] (measured maxima on these fixtures:
-    fp16 1.0e-2 at N=101, bf16 1.35e-1; tools/tc_parity_report.py prints them);
-  * greedy decisions: identical wherever the reference's top-2 log-prob gap exceeds DECISION_GAP[precision]."""
+  * log-probabilities, fp16 operands (the product precision): within 1e-3 RELATIVE of the reference,
+    |dlogp| <= LOGP_RTOL * max(1, |logp_ref|)   (unit floor: a relative bound on a log-probability near 0 would be a
+    bound on rounding noise); measured 5.7e-4 at N = 101 (tools/emulate_tc_precision.py reproduces the kernel's
+    roundings on the CPU: 2.5e-3 absolute at |logp| ~ 4.4);
+  * greedy decisions: identical wherever the reference's top two log-probabilities are not tied within that
+    tolerance, i.e. gap > tol(top1) + tol(top2).
+bf16 operands (8-bit significand) miss the tolerance by an order of magnitude (3.3e-2 absolute at N = 101) and are not
+a supported product precision (Policy refuses them without allow_reduced_accuracy=True); the bf16 rows below only
+characterise that mode with bars taken from its measurement and make no parity claim."""
 import warnings
 
 import numpy as np
@@ -17,10 +22,16 @@ from oracle.replay import env_args, load_case, start_nodes_of
 
 pytestmark = pytest.mark.gpu
 
-LOGP_ATOL = {"fp16": 2.5e-2, "bf16": 2.5e-1}
-DECISION_GAP = {"fp16": 3e-3, "bf16": 5e-2}
-EMB_ATOL = {"fp16": 4e-3, "bf16": 3e-2}      # h_fin / node_emb against the fp32 CUDA path (values are O(1))
+LOGP_RTOL = 1e-3                 # north_star: "log-probabilities ... within 1e-3 relative"
+BF16_LOGP_ATOL = 8e-2            # characterisation only (measured 3.3e-2 .. 4e-2), no parity claim
+BF16_DECISION_GAP = 8e-2
+EMB_ATOL = {"fp16": 4e-3, "bf16": 3e-2}      # h_fin / node_emb against the fp32 CUDA path: an internal quantity of O(1),
+                                             # bounded by the 16-bit operand rounding of six GraphConv blocks
 CASES = ["g21_pomo", "g101_pomo", "g51_sampling", "g51_upd2", "g31_k2"]
+
+
+def logp_tol(ref):
+    return LOGP_RTOL * np.maximum(1.0, np.abs(ref))
 
 
 def _make(g, precision):
@@ -28,12 +39,18 @@ def _make(g, precision):
     from jampr_plus_b200.weights import random_state_dict
     env = RPEnv(inference=True, device="cuda", **env_args(g["env_kwargs"]))
     env.seed(1)
-    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision, allow_reduced_accuracy=True)
     pol.load_state_dict(random_state_dict(int(g["policy_seed"])))
     pol.eval()
     pol.return_logp = True
     env.load_data(g["instances"], dist_mat=torch.from_numpy(g["static_dist"]))
     return env, pol
+
+
+def test_bf16_is_not_a_product_precision():
+    from jampr_plus_b200 import Policy, RPEnv
+    with pytest.raises(NotImplementedError, match="1e-3"):
+        Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="bf16")
 
 
 def _sn(g):
@@ -49,7 +66,7 @@ def test_teacher_forced_tc(name, precision):
     envr, polr = _make(g, "fp32")
     obs, obr = env.reset(start_nodes=_sn(g)), envr.reset(start_nodes=_sn(g))
     T = g["trace_action"].shape[0]
-    worst, flips, n_dec = 0.0, 0, 0
+    worst, worst_rel, flips, n_dec, n_decisive = 0.0, 0.0, 0, 0, 0
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         for t in range(T):
@@ -61,20 +78,26 @@ def test_teacher_forced_tc(name, precision):
             ref = g["trace_logp"][t]
             fin = np.isfinite(ref)
             assert np.array_equal(np.isfinite(lp), fin), f"support step {t}"
-            err = float(np.abs(lp - ref)[fin].max())
-            worst = max(worst, err)
-            assert err <= LOGP_ATOL[precision], (t, err)
+            err = np.abs(lp - ref)[fin]
+            worst = max(worst, float(err.max()))
+            worst_rel = max(worst_rel, float((err / np.maximum(1.0, np.abs(ref[fin]))).max()))
+            if precision == "fp16":
+                assert bool((err <= logp_tol(ref[fin])).all()), (t, float(err.max()), worst_rel)
+            else:
+                assert float(err.max()) <= BF16_LOGP_ATOL, (t, float(err.max()))
             if env._graph_fresh:
                 assert float((env.state["h_fin"] - envr.state["h_fin"]).abs().max()) <= EMB_ATOL[precision], t
                 assert float((env.state["ne"] - envr.state["ne"]).abs().max()) <= EMB_ATOL[precision], t
             if g["decode"] == "greedy":
                 srt = np.sort(ref, -1)
-                decisive = (srt[:, -1] - srt[:, -2]) > DECISION_GAP[precision]
+                gap = srt[:, -1] - srt[:, -2]
+                decisive = gap > (logp_tol(srt[:, -1]) + logp_tol(srt[:, -2]) if precision == "fp16" else BF16_DECISION_GAP)
                 mine = env.state["action"].cpu().numpy()
                 same = (mine == g["trace_action"][t]).all(-1)
                 assert same[decisive].all(), f"decisive greedy action differs at step {t}"
                 flips += int((~same).sum())
                 n_dec += same.size
+                n_decisive += int(decisive.sum())
             act = torch.from_numpy(g["trace_action"][t].astype(np.int64))
             obs, cost, done, _ = env.step(act)
             obr, _, _, _ = envr.step(act)
@@ -82,7 +105,10 @@ def test_teacher_forced_tc(name, precision):
                 assert np.array_equal(cost.cpu().numpy(), g["trace_cost"][t]), f"cost step {t}"
     assert done
     assert np.array_equal(env.tour_plan.cpu().numpy(), g["final_tour_plan"])
-    print(f"{name}/{precision}: worst |dlogp| {worst:.2e}, {flips}/{n_dec} near-tie decisions differ")
+    if g["decode"] == "greedy":
+        assert n_decisive > 0.5 * n_dec, "the decisive set must not be (nearly) empty"
+    print(f"{name}/{precision}: worst |dlogp| {worst:.2e} (relative {worst_rel:.2e}), {flips}/{n_dec} near-tie decisions "
+          f"differ, {n_decisive} decisive")
 
 
 @pytest.mark.parametrize("precision", ["fp16"])
@@ -95,7 +121,7 @@ def test_fused_rollout_tc(name, precision):
     env, pol = _make(g, precision)
     pol.return_logp = False
     srt = np.sort(g["trace_logp"], -1)
-    decided = ((srt[..., -1] - srt[..., -2]) > DECISION_GAP[precision]).all(0)
+    decided = ((srt[..., -1] - srt[..., -2]) > logp_tol(srt[..., -1]) + logp_tol(srt[..., -2])).all(0)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         env.reset(start_nodes=_sn(g))
@@ -176,8 +202,8 @@ def test_tc_matches_fp32_path_other_shapes(n_customers, k_frac, K, P):
             obs1, c1, _, _ = envs[1].step(action)
             assert torch.equal(c0, c1)
             steps += 1
-    assert worst <= LOGP_ATOL["fp16"], worst
-    assert steps > n_customers // 2
+    assert worst <= 2e-2, worst      # against the fp32 CUDA path on shapes without a reference trace: a smoke bound on
+    assert steps > n_customers // 2  # the other tilings (the traced fixtures above carry the parity claim)
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
@@ -191,7 +217,7 @@ def test_tc_rollout_is_deterministic_under_load(precision):
     from jampr_plus_b200.weights import random_state_dict
     inst = sample_instances(512, graph_size=100, seed=9)
     env = RPEnv(max_concurrent_vehicles=3, k_nbh_frac=0.25, pomo=True, num_samples=16, inference=True, device="cuda")
-    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision, allow_reduced_accuracy=True)
     pol.load_state_dict(random_state_dict(2))
     pol.eval()
     outs = []
@@ -207,3 +233,51 @@ def test_tc_rollout_is_deterministic_under_load(precision):
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
     assert torch.isfinite(outs[0][1]).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_seeded_sampling_replays_on_cpu(precision):
+    """Sampling without caller-supplied uniforms: the kernel draws from jampr_uniform(seed, rollout, step)
+    (csrc/common.cuh); oracle/rng.py is its CPU twin, so the episode can be replayed: the inverse-CDF pick of the
+    kernel's own log-probabilities at the twin's uniforms must equal the kernel's action, every step."""
+    from oracle.policy_oracle import select_inverse_cdf
+    from oracle.rng import uniforms
+    g = load_case("g51_sampling")
+    env, pol = _make(g, precision)
+    pol.set_decode_type("sampling")
+    pol.sampling_seed = 987654321
+    obs = env.reset()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        for t in range(25):
+            step_no = env._step
+            action, ll, _ = pol(obs)
+            logp = pol.log_probs(env).cpu()
+            u = torch.from_numpy(uniforms(pol.sampling_seed, env.bs, step_no))
+            act_o, ll_o = select_inverse_cdf(logp, obs.nbh.cpu().long(), u)
+            assert torch.equal(action.cpu(), act_o), f"step {t}"
+            assert torch.equal(ll.cpu(), ll_o)
+            obs, _, done, _ = env.step(action)
+            if done:
+                break
+
+
+def test_two_policies_sharing_one_env_reencode():
+    """The node-encoder output lives in the env's buffers and is precision specific: alternating an fp32 and an fp16
+    policy on one env must give each its own static tables (stale encode_static key)."""
+    g = load_case("g21_pomo")
+    env, p16 = _make(g, "fp16")
+    _, p32 = _make(g, "fp32")
+    env2, q32 = _make(g, "fp32")
+    obs = env.reset(start_nodes=_sn(g))
+    obs2 = env2.reset(start_nodes=_sn(g))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        p32(obs)
+        ref = p32.log_probs(env).clone()
+        p16(obs)
+        p32(obs)                      # must re-encode: the tables were last written by the fp16 policy
+        again = p32.log_probs(env).clone()
+        q32(obs2)
+    assert torch.equal(ref, again)
+    assert torch.equal(ref, q32.log_probs(env2))
