@@ -442,7 +442,7 @@ def main():
         pol.reset_static()
         env.reset()
         st = env.state
-        st.ensure_policy_buffers(False)
+        st.ensure_policy_buffers(False, split=args.precision != "fp32")
         w = pol.encode_static(env)
         lib, d, p, S = pol._lib, env._dims, env._inst, env._stream()
         evs, env_evs = [], []
@@ -493,7 +493,8 @@ def main():
                         "peak": hbm, "unit": "GB/s", "frac": env_bytes / (env_ms * 1e-3) / 1e9 / hbm, "traffic": None,
                         "bytes_per_launch_pair": env_bytes, "avg_ms": env_ms,
                         "share_of_step": env_ms * len(live_env) / (ms_res / args.steps)}
-        roof = {"bound": "tensor", "kernel": "policy_step_tc2 (tour-graph GNN + decoder, fused)" if fused else "tour_encoder_f32",
+        roof = {"bound": "tensor", "kernel": "policy step = policy_step_tc2 (tour-graph GNN, split mode) + decoder_tc (tcgen05 "
+                                             "decoder over 128 rollouts), both launches timed together" if fused else "tour_encoder_f32",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",

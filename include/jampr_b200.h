@@ -8,7 +8,11 @@
  *
  * Conventions
  *  - Every pointer inside the structs is a DEVICE pointer owned by the caller (torch-allocated); the
- *    library allocates nothing persistent, keeps no global state and never synchronises the stream.
+ *    library allocates nothing persistent and never synchronises the stream.  It holds no state between calls
+ *    except two debugging switches that are read ONCE from the process environment on first use and select between
+ *    equivalent kernels (results within the documented tolerances either way): JAMPR_TC_VARIANT (1 = one-CTA-per-SM
+ *    tiling of the fused policy step, 2 = two-CTA tiling with the fused decoder, default 3 = two-CTA tiling + split
+ *    tcgen05 decoder) and JAMPR_NODE_ENCODER=fp32 (CUDA-core node encoder on the 16-bit precisions).
  *  - All calls enqueue work on `stream` (a cudaStream_t passed as void*) and return 0 on success,
  *    a negative JAMPR_E_* code for argument errors, or a positive cudaError_t for launch errors.
  *  - Data-dependent conditions the reference raises on are OR-ed into `status[rollout]`
@@ -30,7 +34,7 @@
 extern "C" {
 #endif
 
-#define JAMPR_ABI_VERSION 3
+#define JAMPR_ABI_VERSION 4
 
 /* argument errors */
 #define JAMPR_E_BADARG   (-1)
@@ -132,6 +136,14 @@ typedef struct {
   void*     hbuf;      /* (2,bs,Npad,128) 16-bit ping-pong tour-graph embedding of the large-graph path (N > 128), or NULL */
   float*    hskip;     /* (bs,Npad,128) fp32 skip operand of the large-graph path, or NULL */
   float*    stats_part;/* (bs,Npad/128,2,256) per-tile column sums / maxima of ne (large-graph path), or NULL */
+  /* split decoder of the tensor-core path (csrc/decoder_tc.cu: the decoder's dense stages as tcgen05 GEMMs over 128
+   * rollouts per CTA).  All six NULL = the decoder stays fused into the per-rollout policy kernel. */
+  void*     ne16;      /* (bs,N,256) 16-bit node_emb rows written by the GNN kernel, gathered by the decoder */
+  float*    dq;        /* (bs,512)   decoder query [mean + mean, max + max] (policy.py:179-182) */
+  float*    dte;       /* (bs,4,256) tour embeddings of the K <= 4 active slots (tour_encoder.py:202-213) */
+  float*    dqp;       /* (bs,4,256) scratch: per-head glimpse query W_gk,h^T ctxt_h */
+  float*    dgbar;     /* (bs,4,256) scratch: per-head glimpse-weighted sum of the action embeddings */
+  float*    dlp;       /* (bs,256)   scratch: logit query W_lk^T out_proj(glimpse) */
 } jampr_state_t;
 
 /* Policy weights: one fp32 blob on the device, packed by jampr_plus_b200/model/packing.py.

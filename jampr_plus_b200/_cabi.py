@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libjampr_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 ST_NO_FEASIBLE, ST_TOUR_OVERFLOW, ST_FLEET_EXHAUSTED, ST_NAN_LOGITS, ST_TW_COLLAPSE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLING = 0, 1
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
@@ -33,7 +33,7 @@ class Instances(C.Structure):
 
 STATE_FIELDS = ("visited", "pred", "succ", "plan", "vflags", "row", "nxt", "cur", "row_last", "cap", "time", "cttd",
                 "total", "cost", "status", "allvis", "nvis", "nbh", "mask", "action", "ll", "entropy", "logp",
-                "h_fin", "ne", "ne_stats", "ctl", "hbuf", "hskip", "stats_part")
+                "h_fin", "ne", "ne_stats", "ctl", "hbuf", "hskip", "stats_part", "ne16", "dq", "dte", "dqp", "dgbar", "dlp")
 
 
 class State(C.Structure):

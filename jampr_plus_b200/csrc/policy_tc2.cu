@@ -379,7 +379,8 @@ __host__ __device__ inline uint32_t p2_r2_bytes(int N, int k, int A) {
 // accumulator row owned by a thread in the epilogue / h_0 phases: TMEM lane quarter = warp & 3
 __device__ __forceinline__ int q4_row(int tid) { return ((tid >> 5) & 3) * 32 + (tid & 31); }
 
-template <typename T>
+// SPLIT = true: stop after the query / tour embeddings and hand the decoder over to decoder_tc.cu
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const PtArgs a) {
   using T2 = typename Elem<T>::T2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -762,6 +763,8 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       if (r < N) {
         const float4* bo = reinterpret_cast<const float4*>(w + OFF_TE_OUT_B + col0);
         float4* gdst = a.store_cache ? reinterpret_cast<float4*>(st.ne + ((size_t)b * N + r) * 256 + col0) : nullptr;
+        uint4* g16 = SPLIT ? reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st.ne16) + (((size_t)b * N + r) * 256 + col0) * 2)
+                             : nullptr;      // split decoder: the 16-bit rows also go to HBM (decoder_tc.cu gathers them)
         uint8_t* dst = s_ne16 + (size_t)r * NE16_STRIDE + col0 * 2;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -771,9 +774,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
           const float2 v2 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(acc[8 * i + 4]), __uint_as_float(acc[8 * i + 5])), make_float2(bb.x, bb.y)), make_float2(sb.x, sb.y));
           const float2 v3 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(acc[8 * i + 6]), __uint_as_float(acc[8 * i + 7])), make_float2(bb.z, bb.w)), make_float2(sb.z, sb.w));
           const float4 va = make_float4(v0.x, v0.y, v1.x, v1.y), vb = make_float4(v2.x, v2.y, v3.x, v3.y);
-          *reinterpret_cast<uint4*>(dst + i * 16) =
-              make_uint4(as_u32(Elem<T>::from2(va.x, va.y)), as_u32(Elem<T>::from2(va.z, va.w)),
-                         as_u32(Elem<T>::from2(vb.x, vb.y)), as_u32(Elem<T>::from2(vb.z, vb.w)));
+          const uint4 pk = make_uint4(as_u32(Elem<T>::from2(va.x, va.y)), as_u32(Elem<T>::from2(va.z, va.w)),
+                                      as_u32(Elem<T>::from2(vb.x, vb.y)), as_u32(Elem<T>::from2(vb.z, vb.w)));
+          *reinterpret_cast<uint4*>(dst + i * 16) = pk;
+          if (g16) g16[i] = pk;
           if (gdst) { gdst[2 * i] = va; gdst[2 * i + 1] = vb; }
         }
       }
@@ -826,7 +830,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   }
   uint4 pre[8];
   float4 pref[8];
-  mvf_prefetch(w + OFF_CTXT_WT, 512, pref);          // first weight batch of stage (c): no dependency, hides its latency
+  if (!SPLIT) mvf_prefetch(w + OFF_CTXT_WT, 512, pref);   // first weight batch of stage (c): no dependency, hides its latency
   if (mv) matvec2<T, 2, 4>(w16 + W16_TO2, 128, smem_u32(s_mean), 128, s_part);     // NV = 4 >= K slots (K <= 4 here)
   // (a) column mean / max of node_emb over the nodes (policy.py:179-181): thread = column pair x row parity
   {
@@ -863,7 +867,15 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     }
     s_q[tid] = nmean + sm / (float)K;
     s_q[256 + tid] = nmax + mx;
+    if (SPLIT) {
+      // split decoder: the query (policy.py:179-182) and the tour embeddings go to HBM; the dense stages (ctxt_proj,
+      // glimpse keys / values, logit keys) run as tcgen05 GEMMs over 128 rollouts in decoder_tc.cu
+      st.dq[(size_t)b * 512 + tid] = s_q[tid];
+      st.dq[(size_t)b * 512 + 256 + tid] = s_q[256 + tid];
+      for (int t = 0; t < K; ++t) st.dte[((size_t)b * 4 + t) * 256 + tid] = s_te[t * 256 + tid];
+    }
   }
+  if (SPLIT) return;
   __syncthreads();
   TL(23);
   // (c) ctxt = ctxt_proj(query)
@@ -1136,17 +1148,17 @@ static size_t p2_smem_bytes(const jampr_dims_t* d) {
   return s;
 }
 
-template <typename T>
+template <typename T, bool SPLIT>
 static int launch_p2(const PtArgs& a, size_t smem, cudaStream_t s) {
-  CUDA_RET(cudaFuncSetAttribute(policy_step_tc2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  policy_step_tc2_kernel<T><<<a.d.n_inst * a.d.n_samples, P2_THREADS, smem, s>>>(a);
+  CUDA_RET(cudaFuncSetAttribute(policy_step_tc2_kernel<T, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  policy_step_tc2_kernel<T, SPLIT><<<a.d.n_inst * a.d.n_samples, P2_THREADS, smem, s>>>(a);
   return launch_status();
 }
 
 // Returns JAMPR_E_TOOLARGE when the configuration does not fit this tiling (caller falls back to policy_tc.cu).
 int jampr_policy_step_tc2(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
                           const jampr_state_t* st, int graph_fresh, int step_no, int decode_type, uint64_t seed,
-                          const float* uniforms, int store_cache, cudaStream_t s) {
+                          const float* uniforms, int store_cache, int split, cudaStream_t s) {
   if (d->n_nodes > 128 || d->n_slots > 4 || d->k_nbh > 127) return JAMPR_E_TOOLARGE;
   if (!w->blob_bf16 || w->n_bf16 < (int64_t)W16_END) return JAMPR_E_BADARG;
   const int N = d->n_nodes, A = d->n_slots * d->k_nbh;
@@ -1167,11 +1179,16 @@ int jampr_policy_step_tc2(const jampr_dims_t* d, const jampr_instances_t* inst, 
   a.decode_type = decode_type;
   a.graph_fresh = graph_fresh;
   a.store_cache = store_cache;
+  a.split = split;
+#ifdef JAMPR_ABLATE_BUILD
   static const int ablate = [] {
     const char* e = getenv("JAMPR_TC_ABLATE");
     return e ? atoi(e) : 0;
   }();
   a.ablate = ablate;
-  if (w->precision == JAMPR_PREC_F16) return launch_p2<__half>(a, smem, s);
-  return launch_p2<__nv_bfloat16>(a, smem, s);
+#else
+  a.ablate = 0;
+#endif
+  if (w->precision == JAMPR_PREC_F16) return split ? launch_p2<__half, true>(a, smem, s) : launch_p2<__half, false>(a, smem, s);
+  return split ? launch_p2<__nv_bfloat16, true>(a, smem, s) : launch_p2<__nv_bfloat16, false>(a, smem, s);
 }

@@ -14,7 +14,17 @@ using namespace tc;
 #define W16_GV (W16_GK + 256 * 256)                     // [256][256]  set_proj rows 256..511, transposed
 #define W16_M1 (W16_GV + 256 * 256)                     // [256][256]  (W_lk^T W_out)^T
 #define W16_NE (W16_M1 + 256 * 256)                     // 20 stages: node-encoder layers 0..2, output_proj halves, TE input proj
-#define W16_END (W16_NE + 20 * W16_STAGE)
+// split-decoder GEMM operands (decoder_tc.cu), B tiles [rows][64 K] in the 128-byte swizzle, a hi part followed by a lo
+// part (w = hi + lo, both 16-bit): ctxt_proj (256 x 512) as 8 K-block tiles; per head B[c][d] = set_proj[64h + d][c]
+// (256 x 64); per head 4 K-block tiles of set_proj[256 + 64h .. +64] (64 x 256); M1 = W_lk^T W_out (256 x 256) as 4 tiles
+#define WD_TILE 16384                                   // elements of a [256 rows][64 K] tile (32 KB)
+#define WD_C 0
+#define WD_GK (WD_C + 8 * WD_TILE)
+#define WD_GV (WD_GK + 4 * WD_TILE)
+#define WD_M1 (WD_GV + 4 * WD_TILE)
+#define WD_PART (WD_M1 + 4 * WD_TILE)                   // elements of one part (hi or lo)
+#define W16_DEC (W16_NE + 20 * W16_STAGE)
+#define W16_END (W16_DEC + 2 * WD_PART)
 
 struct PtArgs {
   jampr_dims_t d;
@@ -28,6 +38,7 @@ struct PtArgs {
   int decode_type;
   int graph_fresh;
   int store_cache;       // write h_fin / ne / ne_stats to HBM (needed when later steps reuse them)
+  int split;             // 1 = stop after the query / tour embeddings and hand over to decoder_tc.cu (st.ne16, dq, dte)
   int ablate;            // timing experiments only (JAMPR_TC_ABLATE): 1 skip kNN aggregation, 2 skip layer epilogue
                          // math, 4 skip the decoder mat-vec chain, 8 skip the MMAs, 16 skip the whole decoder, 32 no wait for weight stages
 };

@@ -13,7 +13,10 @@ int jampr_decoder_launch(const jampr_dims_t*, const jampr_instances_t*, const ja
 int jampr_policy_step_tc(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, const jampr_state_t*,
                          int, int, int, uint64_t, const float*, int, cudaStream_t);
 int jampr_policy_step_tc2(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, const jampr_state_t*,
-                          int, int, int, uint64_t, const float*, int, cudaStream_t);
+                          int, int, int, uint64_t, const float*, int, int, cudaStream_t);
+int jampr_decoder_tc(const jampr_dims_t*, const jampr_weights_t*, const jampr_state_t*, int, int, uint64_t, const float*,
+                     cudaStream_t);
+int jampr_decoder_tc_fits(const jampr_dims_t*);
 int64_t jampr_w16_elems(void);
 int jampr_tc_prepare(const jampr_dims_t*, const jampr_instances_t*, int, cudaStream_t);
 int jampr_lg_node_encoder(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, cudaStream_t);
@@ -21,17 +24,23 @@ int jampr_lg_tour_encoder(const jampr_dims_t*, const jampr_instances_t*, const j
                           int, cudaStream_t);
 #define JAMPR_TILE_NODES 128     // graphs up to this size run the single-tile kernels, larger ones the layer-wise path
 
-// Tensor-core policy step: the two-CTAs-per-SM tiling (policy_tc2.cu) when the graph fits it, else the one-CTA
-// tiling (policy_tc.cu).  JAMPR_TC_VARIANT=1 forces the latter (A/B measurements).
+// Tensor-core policy step.  Default (variant 3): the two-CTAs-per-SM GNN kernel (policy_tc2.cu) in split mode followed
+// by the 128-rollouts-per-CTA tcgen05 decoder (decoder_tc.cu), when the caller supplied the hand-over buffers and the
+// shapes fit; variant 2: the same GNN kernel with the decoder fused per rollout; variant 1 (and graphs that do not fit
+// the two-CTA tiling): the one-CTA tiling (policy_tc.cu).  JAMPR_TC_VARIANT selects (A/B measurements, header).
 static int policy_step_tc_any(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
                               const jampr_state_t* st, int fresh, int step_no, int decode_type, uint64_t seed,
                               const float* uniforms, int store_cache, cudaStream_t s) {
   static const int variant = [] {
     const char* e = getenv("JAMPR_TC_VARIANT");
-    return (e && e[0] == '1') ? 1 : 2;
+    return (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
   }();
-  if (variant == 2) {
-    const int rc = jampr_policy_step_tc2(d, inst, w, st, fresh, step_no, decode_type, seed, uniforms, store_cache, s);
+  if (variant >= 2) {
+    const bool split = variant == 3 && st->ne16 && st->dq && st->dte && st->dqp && st->dgbar && st->dlp &&
+                       jampr_decoder_tc_fits(d);
+    const int rc = jampr_policy_step_tc2(d, inst, w, st, fresh, step_no, decode_type, seed, uniforms, store_cache,
+                                         split ? 1 : 0, s);
+    if (rc == 0 && split) return jampr_decoder_tc(d, w, st, step_no, decode_type, seed, uniforms, s);
     if (rc != JAMPR_E_TOOLARGE) return rc;
   }
   return jampr_policy_step_tc(d, inst, w, st, fresh, step_no, decode_type, seed, uniforms, store_cache, s);

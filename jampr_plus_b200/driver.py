@@ -71,7 +71,7 @@ def rollout(policy, env, max_steps: Optional[int] = None, check: bool = True,
     Returns (total cost (bs,), info) with the reference's info keys."""
     assert env._is_reset, "call env.reset() or env.import_sol() first"
     st = env.state
-    st.ensure_policy_buffers(policy.return_logp)
+    st.ensure_policy_buffers(policy.return_logp, split=policy.precision != "fp32")
     w = policy.encode_static(env)
     cap = env.graph_size + env.max_vehicle_number + 1
     n = cap - env._step + 1 if max_steps is None else max_steps
@@ -107,7 +107,7 @@ def rollout_sharded(policy, env, group=None, reduce_max=None, graph: bool = Fals
     from .sharding import global_done_step
     assert env._is_reset, "call env.reset() or env.import_sol() first"
     st = env.state
-    st.ensure_policy_buffers(policy.return_logp)
+    st.ensure_policy_buffers(policy.return_logp, split=policy.precision != "fp32")
     w = policy.encode_static(env)
     ctl = st["ctl"]
     ctl[_cabi.CTL_HOLD] = 1

@@ -226,7 +226,7 @@ class Policy(nn.Module):
             raise RuntimeError("this Policy consumes observations of jampr_plus_b200.RPEnv (obs.state is missing); "
                                "there is no PyTorch fallback path")
         st = env.state
-        st.ensure_policy_buffers(self.return_logp)
+        st.ensure_policy_buffers(self.return_logp, split=self.precision != "fp32")
         w = self.encode_static(env, recompute_static)
         code = self._decode_code()
         u = None if uniforms is None else uniforms.to(self._device, torch.float32).contiguous()

@@ -132,6 +132,17 @@ def pack_tc(sd: Dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16) ->
     for half in range(2):
         parts.append(sw128_image(wno[half * 128:(half + 1) * 128].contiguous().to(dtype)))
     parts.append(sw128_image(sd["tour_encoder.node_emb_input_proj.weight"].contiguous().to(dtype)))
+    # split decoder (csrc/decoder_tc.cu, WD_*): B operands [rows = outputs][K] as K-block tiles, a hi part followed by a
+    # lo part with w = hi + lo (both 16-bit): every dense decoder stage runs hi*hi + lo*hi + hi*lo on the tensor cores
+    m1 = (sp[512:768].double().t() @ sd["decoder.out_proj.weight"].double()).float()      # lp = M1 g, M1 = W_lk^T W_out
+    mats = [sd["decoder.ctxt_proj.weight"]]                                                # (256, 512): 8 tiles
+    mats += [sp[64 * h:64 * h + 64, :].t().contiguous() for h in range(4)]                 # (256, 64) per head: qp_h = B ctxt_h
+    mats += [sp[256 + 64 * h:256 + 64 * h + 64, :].contiguous() for h in range(4)]         # (64, 256) per head: 4 tiles each
+    mats += [m1]                                                                           # (256, 256): 4 tiles
+    hi = [m.to(dtype) for m in mats]
+    lo = [(m - h_.float()).to(dtype) for m, h_ in zip(mats, hi)]
+    for part in (hi, lo):
+        parts.extend(sw128_image(m.contiguous()) for m in part)
     blob = torch.cat(parts)
     lib = _cabi.load_library()
     assert blob.numel() == lib.jampr_weight_blob16_elems(), (blob.numel(), lib.jampr_weight_blob16_elems())

@@ -93,6 +93,16 @@ _POLICY_SPEC = {
     "ne": (torch.float32, lambda s: (s.bs, s.N, 256)),
     "ne_stats": (torch.float32, lambda s: (s.bs, 2, 256)),
 }
+# split decoder of the tensor-core path (csrc/decoder_tc.cu): hand-over buffers between the per-rollout GNN kernel and
+# the 128-rollouts-per-CTA decoder kernel; allocated when a 16-bit policy drives a graph that fits one tile
+_SPLIT_SPEC = {
+    "ne16": (torch.int16, lambda s: (s.bs, s.N, 256)),
+    "dq": (torch.float32, lambda s: (s.bs, 512)),
+    "dte": (torch.float32, lambda s: (s.bs, 4, 256)),
+    "dqp": (torch.float32, lambda s: (s.bs, 4, 256)),
+    "dgbar": (torch.float32, lambda s: (s.bs, 4, 256)),
+    "dlp": (torch.float32, lambda s: (s.bs, 256)),
+}
 # large-graph path only (N > 128: the graph spans several 128-row tiles, csrc/gnn_large.cu)
 _LARGE_SPEC = {
     "hbuf": (torch.int16, lambda s: (2, s.bs, (s.N + 127) // 128 * 128, 128)),
@@ -115,8 +125,13 @@ class DeviceState:
         self._struct = None
         self.graphs = {}      # captured CUDA graphs of rollouts over these buffers (driver._replay_or_capture)
 
-    def ensure_policy_buffers(self, want_logp: bool = False):
+    def ensure_policy_buffers(self, want_logp: bool = False, split: bool = False):
         changed = False
+        if split and self.N <= 128 and self.K <= 4:
+            for name, (dt, shp) in _SPLIT_SPEC.items():
+                if name not in self.t:
+                    self.t[name] = self._alloc.zeros(shp(self), dt, self.device, name)
+                    changed = True
         for name, (dt, shp) in _POLICY_SPEC.items():
             if name == "logp" and not (want_logp or self.want_logp):
                 continue

@@ -99,74 +99,94 @@ def _load_workload(name):
 
 
 def test_production_configuration_fp16_against_fp32():
-    """The benchmarked configuration itself (BASELINE config 2: the reference generator's 4096 all_1_low instances x
-    16 POMO samples, fused device loop replayed as a CUDA graph, no log-probability output, idle-rollout skip) on the
-    fp16 tensor-core path against the fp32 CUDA-core path (the 1e-5 anchor) from identical start nodes:
-      * rollouts whose fp32 decisions are ALL decisive (top-2 log-prob gap above twice the 1e-3-relative tolerance at
-        every step) must produce identical tours — the set is asserted to be non-empty;
-      * cost level: mean per-instance best cost within 1e-3 relative; per-instance best cost within 1e-3 relative for
-        the large majority of instances (a flipped near-tie changes a tour, not the cost level).
-    The fp32 side runs on a 512-instance slice (it is 6x slower and steps through the host API to expose its
-    log-probabilities); the fp16 side runs all 65,536 rollouts in the production mode."""
+    """The benchmarked configuration itself (BASELINE config 2: the reference generator's all_1_low instances x 16 POMO
+    samples; no log-probability output, so the kernel runs without the embedding cache stores and with the
+    idle-rollout skip) on the fp16 tensor-core path against the fp32 CUDA-core path (the 1e-5 anchor):
+      1. teacher forced on 512 instances (8192 rollouts, ~1 M decisions): both environments follow the fp32 policy's
+         greedy actions; at every step the fp16 policy, in the production configuration, must pick the same action
+         wherever the fp32 top-2 log-prob gap exceeds the two 1e-3-relative tolerances (the decisive set is most of the
+         decisions, asserted), and its log-likelihood of that action must be within the tolerance;
+      2. free running, all 4096 instances (65,536 rollouts) through the fused device loop replayed as a CUDA graph:
+         the replay reproduces the eager episode bit for bit, and the cost level (mean per-instance best cost) agrees
+         with the fp32 path's free-running episode on the 512-instance slice within 1e-3 relative — a flipped near-tie
+         changes a tour, not the cost level."""
     from jampr_plus_b200 import Policy, RPEnv
     from jampr_plus_b200.driver import rollout
     from jampr_plus_b200.weights import random_state_dict
     host, kv = _load_workload("workload_all_1_low_4096.npz")
     I, P, Iref = 4096, 16, 512
     kw = dict(max_concurrent_vehicles=3, k_nbh_frac=0.25, pomo=True, num_samples=P, inference=True, device="cuda")
-    env = RPEnv(**kw)
-    env.seed(1235)
-    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp16")
-    pol.load_state_dict(random_state_dict(0))
-    pol.eval()
-    env.load_arrays({k: v.cuda() for k, v in host.items()}, kv)
+
+    def make(prec, logp):
+        e = RPEnv(**kw)
+        e.seed(1235)
+        p = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=prec)
+        p.load_state_dict(random_state_dict(0))
+        p.eval()
+        p.return_logp = logp
+        return e, p
+
+    # ---- 1. teacher forced, production kernel configuration on the fp16 side
+    env16, pol16 = make("fp16", False)
+    env32, pol32 = make("fp32", True)
+    sl = {k: v[:Iref].cuda() for k, v in host.items()}
+    env16.load_arrays(sl, kv)
+    env32.load_arrays(sl, kv)
+    n_dec = n_live = n_flip = 0
+    worst_ll = 0.0
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
+        o32 = env32.reset()
+        sn_slice = env32._start_nodes.clone()
+        o16 = env16.reset(start_nodes=sn_slice)
+        done = False
+        while not done:
+            a32, ll32, _ = pol32(o32)
+            a16, ll16, _ = pol16(o16)
+            top = pol32.log_probs(env32).topk(2, dim=-1).values
+            tol = 1e-3 * (top[:, 0].abs().clamp_min(1.0) + top[:, 1].abs().clamp_min(1.0))
+            live = ~(env32.state["allvis"].bool() & (env32.state["cur"] == 0).all(-1))   # idle rollouts decide nothing
+            decisive = live & (((top[:, 0] - top[:, 1]) > tol) | ~torch.isfinite(top[:, 1]))
+            same = (a16 == a32).all(-1)
+            assert bool(same[decisive].all()), "a decisive greedy action differs between the fp16 and the fp32 path"
+            err = (ll16 - ll32).abs().view(-1)[decisive & same]
+            bound = 1e-3 * ll32.abs().view(-1).clamp_min(1.0)[decisive & same]
+            assert bool((err <= bound).all()), float((err / bound).max())
+            worst_ll = max(worst_ll, float((err / bound).max()) if err.numel() else 0.0)
+            n_dec += int(decisive.sum())
+            n_live += int(live.sum())
+            n_flip += int((live & ~same).sum())
+            o32, c32, done, _ = env32.step(a32)
+            o16, c16, _, _ = env16.step(a32)
+            assert torch.equal(c32, c16)
+    assert n_dec > 0.8 * n_live, (n_dec, n_live)
+    assert torch.equal(env16.tour_plan, env32.tour_plan)
+    # ---- 2. free running at full size, CUDA-graph replay
+    env, pol = make("fp16", False)
+    dev_arrays = {k: v.cuda() for k, v in host.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        env.load_arrays(dev_arrays, kv)
         env.reset()
         sn = env._start_nodes.clone()
         total, info = rollout(pol, env, graph=True)
         assert info["done_step"] >= 0
-        # replay of the captured graph gives the same episode
-        env.load_arrays({k: v.cuda() for k, v in host.items()}, kv)
+        total = total.clone()
+        plan = env.tour_plan.clone()
+        env.load_arrays(dev_arrays, kv)
         env.reset(start_nodes=sn)
-        total_b, _ = rollout(pol, env, graph=True)
-        assert torch.equal(total, total_b)
-    best16, _, _ = env.gather_best()
-    plan16 = env.tour_plan[: Iref * P].clone()
-    best16 = best16.clone()
-    true16 = env.true_cost().view(I, P).min(1).values.clone()
-    # ---- fp32 anchor on the first Iref instances, same start nodes, stepping API with log-probabilities
-    envr = RPEnv(**kw)
-    polr = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp32")
-    polr.load_state_dict(random_state_dict(0))
-    polr.eval()
-    polr.return_logp = True
-    envr.load_arrays({k: v[:Iref].cuda() for k, v in host.items()}, kv)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", RuntimeWarning)
-        obs = envr.reset(start_nodes=sn[: Iref * P])
-        decisive = torch.ones(Iref * P, dtype=torch.bool, device="cuda")
-        done = False
-        while not done:
-            action, _, _ = polr(obs)
-            top = polr.log_probs(envr).topk(2, dim=-1).values
-            tol = 1e-3 * (top[:, 0].abs().clamp_min(1.0) + top[:, 1].abs().clamp_min(1.0))
-            live = ~(envr.state["allvis"].bool() & (envr.state["cur"] == 0).all(-1))     # idle rollouts decide nothing
-            decisive &= ~live | ((top[:, 0] - top[:, 1]) > 2.0 * tol) | ~torch.isfinite(top[:, 1])
-            obs, _, done, _ = envr.step(action)
-    plan32 = envr.tour_plan
-    same = (plan16 == plan32).all(-1).all(-1)
-    n_dec = int(decisive.sum())
-    assert n_dec >= 50, f"only {n_dec} fully decisive rollouts: the check would be vacuous"
-    assert bool(same[decisive].all()), f"{int((~same[decisive]).sum())} of {n_dec} decisive rollouts differ"
-    best32, _, _ = envr.gather_best()
-    b16 = best16[:Iref]
-    rel = ((b16 - best32).abs() / best32.abs().clamp_min(1e-6))
-    mean_rel = float((b16.mean() - best32.mean()).abs() / best32.mean())
+        total_b, _ = rollout(pol, env, graph=True)          # second call replays the captured graph
+        assert torch.equal(total, total_b) and torch.equal(plan, env.tour_plan)
+        best16 = env.gather_best()[0][:Iref].clone()
+        assert torch.isfinite(env.true_cost()).all()
+        envr, polr = make("fp32", False)
+        envr.load_arrays(sl, kv)
+        envr.reset(start_nodes=sn[: Iref * P])
+        rollout(polr, envr)
+        best32 = envr.gather_best()[0]
+    mean_rel = float((best16.mean() - best32.mean()).abs() / best32.mean())
+    frac_same = float((best16 == best32).float().mean())
+    print(f"fp16 vs fp32, production configuration: {n_dec} decisive of {n_live} live decisions all identical "
+          f"({n_flip} near-tie flips), log-likelihood error up to {worst_ll:.2f} of the 1e-3 tolerance; free running: "
+          f"per-instance best cost identical for {frac_same:.3f} of the instances, mean differs by {mean_rel:.2e} relative")
     assert mean_rel <= 1e-3, mean_rel
-    frac_close = float((rel <= 1e-3).float().mean())
-    print(f"fp16 vs fp32 at production size: {n_dec}/{Iref * P} fully decisive rollouts, all with identical tours; "
-          f"{float(same.float().mean()):.3f} of all tours identical; per-instance best cost within 1e-3 relative for "
-          f"{frac_close:.3f} of the instances, mean best cost differs by {mean_rel:.2e} relative")
-    assert frac_close >= 0.5
-    assert torch.isfinite(true16).all()

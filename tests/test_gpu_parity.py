@@ -440,7 +440,7 @@ def test_sharded_rollout_reproduces_union_batch_totals(name, precision):
         from jampr_plus_b200 import _cabi
         for i, e in enumerate(parts):
             st = e.state
-            st.ensure_policy_buffers(pol.return_logp)
+            st.ensure_policy_buffers(pol.return_logp, split=pol.precision != "fp32")
             w = pol.encode_static(e)
             st["ctl"][_cabi.CTL_HOLD] = 1
             cap = e.graph_size + e.max_vehicle_number + 1
