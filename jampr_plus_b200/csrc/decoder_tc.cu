@@ -25,6 +25,7 @@
 #define DT_THREADS 512
 #define DT_WARPS (DT_THREADS / 32)
 #define DT_M 128
+#define DT_BATCH 8             // node-embedding rows in flight per lane in the per-rollout passes
 #define DT_ITEMS 32            // B tiles consumed: 8 (stage A) + 4 (B) + 16 (D) + 4 (E)
 
 struct DtArgs {
@@ -288,27 +289,37 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       if ((lane & 7) == 0) s_qt[(((lane >> 4) << 1) | ((lane >> 3) & 1)) * 4 + t] = z;
     }
     __syncwarp();
-    // pass 1: scores of the feasible actions
+    // pass 1: scores of the feasible actions.  The rows come from HBM / L2 (~1 us): DT_BATCH independent 16-byte loads
+    // per lane are issued back to back before the first is consumed (Little: ~30 KB in flight per SM are needed)
     const T* rows = ne16 + (size_t)b * N * 256 + lane * 8;
-#pragma unroll 2
-    for (int i = 0; i < cnt; ++i) {
-      const int e = s_list[i];
-      const uint4 raw = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[e] * 256);
-      const float2 v0 = Elem<T>::to2(from_u32<T2>(raw.x)), v1 = Elem<T>::to2(from_u32<T2>(raw.y));
-      const float2 v2 = Elem<T>::to2(from_u32<T2>(raw.z)), v3 = Elem<T>::to2(from_u32<T2>(raw.w));
-      float dd[4];
+#pragma unroll 1
+    for (int i0 = 0; i0 < cnt; i0 += DT_BATCH) {
+      uint4 raw[DT_BATCH];
+      int ee[DT_BATCH];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        float2 acc = __ffma2_rn(v0, qv[h][0], make_float2(0.0f, 0.0f));
-        acc = __ffma2_rn(v1, qv[h][1], acc);
-        acc = __ffma2_rn(v2, qv[h][2], acc);
-        acc = __ffma2_rn(v3, qv[h][3], acc);
-        dd[h] = acc.x + acc.y;
+      for (int j = 0; j < DT_BATCH; ++j) {
+        const int i = min(i0 + j, cnt - 1);
+        ee[j] = s_list[i];
+        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[ee[j]] * 256);
       }
-      const float z = warp_sum4(dd[0], dd[1], dd[2], dd[3], lane);
-      if ((lane & 7) == 0) {
-        const int h = ((lane >> 4) << 1) | ((lane >> 3) & 1);
-        s_p[i * 4 + h] = (z + s_qt[h * 4 + e / k]) * 0.125f;
+#pragma unroll
+      for (int j = 0; j < DT_BATCH; ++j) {
+        const float2 v0 = Elem<T>::to2(from_u32<T2>(raw[j].x)), v1 = Elem<T>::to2(from_u32<T2>(raw[j].y));
+        const float2 v2 = Elem<T>::to2(from_u32<T2>(raw[j].z)), v3 = Elem<T>::to2(from_u32<T2>(raw[j].w));
+        float dd[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float2 acc = __ffma2_rn(v0, qv[h][0], make_float2(0.0f, 0.0f));
+          acc = __ffma2_rn(v1, qv[h][1], acc);
+          acc = __ffma2_rn(v2, qv[h][2], acc);
+          acc = __ffma2_rn(v3, qv[h][3], acc);
+          dd[h] = acc.x + acc.y;
+        }
+        const float z = warp_sum4(dd[0], dd[1], dd[2], dd[3], lane);
+        if ((lane & 7) == 0 && i0 + j < cnt) {
+          const int h = ((lane >> 4) << 1) | ((lane >> 3) & 1);
+          s_p[(i0 + j) * 4 + h] = (z + s_qt[h * 4 + ee[j] / k]) * 0.125f;
+        }
       }
     }
     __syncwarp();
@@ -334,31 +345,52 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     for (int h = 0; h < 4; ++h)
 #pragma unroll
       for (int j = 0; j < 4; ++j) g[h][j] = make_float2(0.0f, 0.0f);
-    int cur_t = -1;
-    float2 t0 = make_float2(0.0f, 0.0f), t1 = t0, t2 = t0, t3 = t0;
     const uint32_t p_saddr = smem_u32(s_p);
-#pragma unroll 2
-    for (int i = 0; i < cnt; ++i) {
-      const int e = s_list[i];
-      const int t = e / k;
-      if (t != cur_t) {
-        const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
-        const float4 x = p[0], y = p[1];
-        t0 = make_float2(x.x, x.y); t1 = make_float2(x.z, x.w); t2 = make_float2(y.x, y.y); t3 = make_float2(y.z, y.w);
-        cur_t = t;
+    // tour-embedding part first: gbar_h += P_h[t] tour_emb[t], P_h[t] = sum of p_h over the actions of slot t
+    for (int t = 0; t < K; ++t) {
+      float ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int i = lane; i < cnt; i += 32) {
+        if (s_list[i] / k == t) {
+          const float4 pw = lds_f32x4(p_saddr + (uint32_t)i * 16u);
+          ps[0] += pw.x; ps[1] += pw.y; ps[2] += pw.z; ps[3] += pw.w;
+        }
       }
-      const uint4 raw = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[e] * 256);
-      const float2 v0 = __fadd2_rn(Elem<T>::to2(from_u32<T2>(raw.x)), t0), v1 = __fadd2_rn(Elem<T>::to2(from_u32<T2>(raw.y)), t1);
-      const float2 v2 = __fadd2_rn(Elem<T>::to2(from_u32<T2>(raw.z)), t2), v3 = __fadd2_rn(Elem<T>::to2(from_u32<T2>(raw.w)), t3);
-      const float4 pw = lds_f32x4(p_saddr + (uint32_t)i * 16u);
-      const float ph[4] = {pw.x, pw.y, pw.z, pw.w};
+      const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
+      const float4 x = p[0], y = p[1];
+      const float2 t0 = make_float2(x.x, x.y), t1 = make_float2(x.z, x.w), t2 = make_float2(y.x, y.y), t3 = make_float2(y.z, y.w);
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const float2 p2 = f2(ph[h]);
-        g[h][0] = __ffma2_rn(p2, v0, g[h][0]);
-        g[h][1] = __ffma2_rn(p2, v1, g[h][1]);
-        g[h][2] = __ffma2_rn(p2, v2, g[h][2]);
-        g[h][3] = __ffma2_rn(p2, v3, g[h][3]);
+        const float2 p2 = f2(warp_sum(ps[h]));
+        g[h][0] = __ffma2_rn(p2, t0, g[h][0]);
+        g[h][1] = __ffma2_rn(p2, t1, g[h][1]);
+        g[h][2] = __ffma2_rn(p2, t2, g[h][2]);
+        g[h][3] = __ffma2_rn(p2, t3, g[h][3]);
+      }
+    }
+#pragma unroll 1
+    for (int i0 = 0; i0 < cnt; i0 += DT_BATCH) {
+      uint4 raw[DT_BATCH];
+#pragma unroll
+      for (int j = 0; j < DT_BATCH; ++j) {
+        const int i = min(i0 + j, cnt - 1);
+        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[s_list[i]] * 256);
+      }
+#pragma unroll
+      for (int j = 0; j < DT_BATCH; ++j) {
+        if (i0 + j < cnt) {        // warp-uniform
+          const float2 v0 = Elem<T>::to2(from_u32<T2>(raw[j].x)), v1 = Elem<T>::to2(from_u32<T2>(raw[j].y));
+          const float2 v2 = Elem<T>::to2(from_u32<T2>(raw[j].z)), v3 = Elem<T>::to2(from_u32<T2>(raw[j].w));
+          const float4 pw = lds_f32x4(p_saddr + (uint32_t)(i0 + j) * 16u);
+          const float ph[4] = {pw.x, pw.y, pw.z, pw.w};
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float2 p2 = f2(ph[h]);
+            g[h][0] = __ffma2_rn(p2, v0, g[h][0]);
+            g[h][1] = __ffma2_rn(p2, v1, g[h][1]);
+            g[h][2] = __ffma2_rn(p2, v2, g[h][2]);
+            g[h][3] = __ffma2_rn(p2, v3, g[h][3]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -443,18 +475,27 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     }
     __syncwarp();
     const T* rows = ne16 + (size_t)b * N * 256 + lane * 8;
-#pragma unroll 2
-    for (int i = 0; i < cnt; ++i) {
-      const int e = s_list[i];
-      const uint4 raw = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[e] * 256);
-      float2 acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw.x)), lv[0], make_float2(0.0f, 0.0f));
-      acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw.y)), lv[1], acc);
-      acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw.z)), lv[2], acc);
-      acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw.w)), lv[3], acc);
-      const float z = warp_sum(acc.x + acc.y);
-      const int t = e / k;
-      const float ltv = (t == 0) ? lt[0] : (t == 1) ? lt[1] : (t == 2) ? lt[2] : lt[3];
-      if (lane == 0) s_logit[e] = 10.0f * tanhf((z + ltv) * 0.0625f);
+#pragma unroll 1
+    for (int i0 = 0; i0 < cnt; i0 += DT_BATCH) {
+      uint4 raw[DT_BATCH];
+      int ee[DT_BATCH];
+#pragma unroll
+      for (int j = 0; j < DT_BATCH; ++j) {
+        const int i = min(i0 + j, cnt - 1);
+        ee[j] = s_list[i];
+        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[ee[j]] * 256);
+      }
+#pragma unroll
+      for (int j = 0; j < DT_BATCH; ++j) {
+        float2 acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].x)), lv[0], make_float2(0.0f, 0.0f));
+        acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].y)), lv[1], acc);
+        acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].z)), lv[2], acc);
+        acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].w)), lv[3], acc);
+        const float z = warp_sum(acc.x + acc.y);
+        const int t = ee[j] / k;
+        const float ltv = (t == 0) ? lt[0] : (t == 1) ? lt[1] : (t == 2) ? lt[2] : lt[3];
+        if (lane == 0 && i0 + j < cnt) s_logit[ee[j]] = 10.0f * tanhf((z + ltv) * 0.0625f);
+      }
     }
     __syncwarp();
     // ---- masked log-softmax + selection, same rules as decoder.cu / policy_tc2.cu
