@@ -204,6 +204,36 @@ JAMPR_API int jampr_env_resume(const jampr_dims_t* d, const jampr_instances_t* i
 JAMPR_API int jampr_env_import_finish(const jampr_dims_t* d, const jampr_instances_t* inst,
                             const jampr_state_t* st, int32_t* max_step_out, void* stream);
 
+/* RPEnv.import_sol (env.py:575-706, _recompute_cost :708-718) from DENSE tours instead of nested Python lists: tours
+ * (n_sol, n_tours, tour_len) int16 customers in visiting order, zero padded; kind (n_sol, n_tours) uint8: 0 = no tour,
+ * 1 = complete tour (the list form starts and ends at the depot), 2 = partial tour (open list; fewer than two customers
+ * = dropped like the reference drops singletons).  Rollout b reads solution src_index[b] (NULL = b): bootstrap of the
+ * selected solutions back to num_samples (lns.py:304-310) and _expand_sample_dimension (env.py:1204-1219) are index maps.
+ * Fills plan / vflags / row / nxt / cur / cap / time / cttd / total (total_in (bs) overrides the recomputed totals, the
+ * `cost` argument of import_sol); follow with jampr_env_import_finish for visited / links / observation / step. */
+JAMPR_API int jampr_env_import_tours(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_state_t* st,
+                           const int16_t* tours, const uint8_t* kind, int32_t n_tours, int32_t tour_len,
+                           const int32_t* src_index, const float* total_in, void* stream);
+
+/* The destruction operator on tour buffers — what the reference left as a NotImplemented stub (env.py:720-723, "tensor-based
+ * native destruction operator circumventing expensive conversion to lists") — for lib/lns/destructor.py:86-205
+ * `random_from_route`: per solution pick num_partial tours with more than one customer and mutilate them (random_nodes /
+ * random_cut / const_cut), drop singleton tours, remove max(round(frac_complete * n), 1) of the remaining complete
+ * tours (random or smallest).  Random numbers: jampr_uniform(seed, rollout, iteration * 8192 + draw), restated in
+ * oracle/destroy_oracle.py.  src_plan (n_src, K_max, L) tour buffers; rollout b mutilates solution src_index[b];
+ * output in the dense format of jampr_env_import_tours with n_tours = K_max, tour_len = L (complete tours first). */
+typedef struct {
+  int32_t  num_partial;        /* tours to mutilate per solution */
+  int32_t  rm_partial_mode;    /* 0 random_nodes, 1 random_cut, 2 const_cut, 3 one of the three at random per tour */
+  int32_t  rm_complete_mode;   /* 0 random, 1 smallest */
+  float    frac_partial;       /* frac_rm_nodes_from_partial, in [0, 1) */
+  float    frac_complete;      /* frac_rm_complete_routes, in [0, 1) */
+  int32_t  iteration;          /* LNS step: selects the random stream */
+  uint64_t seed;
+} jampr_destroy_t;
+JAMPR_API int jampr_lns_destroy(const jampr_dims_t* d, const int16_t* src_plan, const int32_t* src_index,
+                      const jampr_destroy_t* prm, int16_t* tours, uint8_t* kind, void* stream);
+
 /* Policy.forward for one step (policy.py:120-227; tour_encoder.py:159-243; attn_decoder.py:62-98):
  * tour-graph GNN (or cached embedding), tour embeddings, pointer attention, masked log-softmax,
  * greedy argmax or inverse-CDF sampling.  graph_fresh: 1 = rebuild the tour-graph embedding,

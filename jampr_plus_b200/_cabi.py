@@ -45,10 +45,19 @@ class Weights(C.Structure):
                 ("precision", C.c_int32), ("reserved", C.c_int32)]
 
 
+class Destroy(C.Structure):
+    _fields_ = [("num_partial", C.c_int32), ("rm_partial_mode", C.c_int32), ("rm_complete_mode", C.c_int32),
+                ("frac_partial", C.c_float), ("frac_complete", C.c_float), ("iteration", C.c_int32),
+                ("seed", C.c_uint64)]
+
+
+RM_PARTIAL_MODES = {"random_nodes": 0, "random_cut": 1, "const_cut": 2, "random": 3}
+RM_COMPLETE_MODES = {"random": 0, "smallest": 1}
+
 SYMBOLS = ("jampr_abi_version", "jampr_weight_blob_floats", "jampr_weight_blob16_elems", "jampr_weight_offsets", "jampr_setup_instances",
            "jampr_node_encoder", "jampr_env_reset", "jampr_env_step", "jampr_env_resume", "jampr_env_import_finish",
            "jampr_tour_encoder", "jampr_policy_step", "jampr_rollout", "jampr_gather_best", "jampr_true_cost",
-           "jampr_selftest_umma")
+           "jampr_selftest_umma", "jampr_env_import_tours", "jampr_lns_destroy")
 
 _lib = None
 
@@ -78,6 +87,8 @@ def load_library():
     lib.jampr_gather_best.argtypes = [PD, PS, _p, _p, _p, _p]
     lib.jampr_true_cost.argtypes = [PD, PI, PS, _p, _p]
     lib.jampr_selftest_umma.argtypes = [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, _p]
+    lib.jampr_env_import_tours.argtypes = [PD, PI, PS, _p, _p, C.c_int32, C.c_int32, _p, _p, _p]
+    lib.jampr_lns_destroy.argtypes = [PD, _p, _p, C.POINTER(Destroy), _p, _p, _p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("jampr_weight_blob_floats", "jampr_weight_blob16_elems"):

@@ -414,8 +414,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_import_kernel(jampr_dims_t d,
       for (int t = 0; t < K; ++t)
         if (s.row[(size_t)b * K + t] == r && (fl & 1)) s.row_last[(size_t)b * K + t] = prev;
     }
-    s.nvis[b] = nvis;
-    s.status[b] = 0;
+    s.nvis[b] = nvis;            // s.status was set by whoever filled the buffers (jampr_env_import_tours or the caller)
     s.allvis[b] = (nvis == N - 1);
     if (nvis == N - 1) atomicAdd(s.ctl + JAMPR_CTL_N_ALLVIS, 1);
     atomicMax(max_step_out, nvis + nfin);

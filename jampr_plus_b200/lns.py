@@ -133,6 +133,7 @@ class LNS:
         self.horizon = float(instance.org_service_horizon)
         self.best_solution, self.best_cost, self.best_true_cost, self.best_step = None, float("inf"), float("inf"), -1
         self.step = 0
+        self.seed = seed
         self.history: List[Tuple[float, float, float]] = []      # (seconds, incumbent env cost, incumbent true cost)
         env.seed(seed)
 
@@ -170,6 +171,99 @@ class LNS:
             w = int(np.argmax(costs))
             sols[w], costs[w], true_costs[w] = deepcopy(self.best_solution), self.best_cost, self.best_true_cost
         return sols, costs, true_costs
+
+    # ------------------------------------------------------------------ the same loop with every solution on the device
+    @torch.no_grad()
+    def search_device(self, time_limit: Optional[float] = None, num_steps: Optional[int] = None,
+                      group=None) -> Tuple[torch.Tensor, float, float]:
+        """construct -> [select -> add incumbent -> bootstrap -> destroy -> import -> repair]* with tour buffers that
+        never leave the device (``RPEnv.destruct``: selection mode "random", the destructor's random_from_route family).
+        Per iteration the host reads two scalars (the new step counter, the incumbent cost for the history).
+
+        ``group`` / an initialised default process group with more than one rank: BASELINE config 5 — instance and
+        weights replicated, every rank mutilates and repairs its own ``num_samples`` sub-problems with its own random
+        streams; after each repair the ranks all_gather their ``num_best + num_other`` cheapest candidates (cost + tour
+        buffer, ~3.6 KB each, NCCL over NVLink; gloo in the CPU tests), every rank keeps the globally cheapest
+        ``num_best`` plus ``num_other`` others drawn with a shared seed as the sources of its next iteration.
+        Returns (incumbent tour buffer (K_max, L) int16, incumbent env cost, incumbent true cost), original units."""
+        import torch.distributed as dist
+        assert time_limit is not None or num_steps is not None
+        env, pol, ds = self.env, self.policy, self.ds
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        n_sel = self.num_best + self.num_other
+        t0 = time.time()
+        pol.set_decode_type("greedy")
+        pol.reset_static()
+        env.load_data([self.inst])
+        env.reset()
+        rollout(pol, env, graph=self.use_graph)
+        kw = dict(num_best=self.num_best, num_other=self.num_other, num_partial=ds.num_partial,
+                  rm_partial_mode=ds.rm_partial_mode, rm_complete_mode=ds.rm_complete_mode,
+                  frac_rm_nodes_from_partial=ds.frac_p, frac_rm_complete_routes=ds.frac_c,
+                  seed=self.seed * 1000003 + rank)
+        inc_cost = torch.full((1,), float("inf"), device=env.device)
+        inc_true = torch.full((1,), float("inf"), device=env.device)
+        inc_plan = torch.zeros(1, env.state.K_max, env.state.L, dtype=torch.int16, device=env.device)
+        gen = torch.Generator(device="cpu").manual_seed(self.seed)       # shared by all ranks: same "others"
+
+        def incumbent_update():
+            cost, idx, plan = env.gather_best()
+            true = env.true_cost().view(1, -1).gather(1, idx.long().view(1, 1)).view(1) * self.horizon
+            better = cost < inc_cost
+            inc_cost.copy_(torch.where(better, cost, inc_cost))
+            inc_true.copy_(torch.where(better, true, inc_true))
+            inc_plan.copy_(torch.where(better.view(1, 1, 1), plan, inc_plan))
+
+        def global_sources():
+            """Sharded selection (sharding.lns_exchange) + the incumbent rule of lns.py:209-222."""
+            from .sharding import lns_exchange
+            costs, src = lns_exchange(env.state["total"], env.state["plan"], self.num_best, self.num_other, gen, group)
+            if self.add_best and not bool((costs == inc_cost).any()):
+                src[costs.argmax()] = inc_plan[0]
+            return src.unsqueeze(0)
+
+        def sync_incumbent():
+            if world == 1:
+                return
+            c = [torch.empty_like(inc_cost) for _ in range(world)]
+            dist.all_gather(c, inc_cost, group=group)
+            best_rank = int(torch.cat(c).argmin())
+            src = dist.get_global_rank(group, best_rank) if group is not None else best_rank
+            for t in (inc_cost, inc_true, inc_plan.view(torch.uint8)):      # int16 is not a collective dtype
+                dist.broadcast(t, src=src, group=group)
+
+        incumbent_update()
+        sync_incumbent()
+        hz = self.horizon
+        self.history.append((time.time() - t0, float(inc_cost) * hz, float(inc_true)))
+        slowest = 0.0
+        while True:
+            if num_steps is not None and self.step >= num_steps:
+                break
+            if time_limit is not None:
+                stop = (time.time() - t0) >= max(time_limit - slowest, 0.0)
+                if world > 1:        # every rank must leave the loop in the same iteration
+                    flag = torch.tensor([int(stop)], device=env.device)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+                    stop = bool(flag.item())
+                if stop:
+                    break
+            ts = time.time()
+            self.step += 1
+            if world > 1:
+                env.destruct(sources=global_sources(), iteration=self.step, **kw)
+            else:
+                env.destruct(iteration=self.step, incumbent_plan=inc_plan if self.add_best else None,
+                             incumbent_cost=inc_cost, **kw)
+            rollout(pol, env, graph=self.use_graph)
+            incumbent_update()
+            sync_incumbent()
+            slowest = max(slowest, time.time() - ts)
+            self.history.append((time.time() - t0, float(inc_cost) * hz, float(inc_true)))
+        self.best_cost, self.best_true_cost = float(inc_cost) * hz, float(inc_true)
+        self.best_plan = inc_plan[0].clone()
+        return self.best_plan, self.best_cost, self.best_true_cost
 
     def search(self, time_limit: Optional[float] = None, num_steps: Optional[int] = None):
         assert time_limit is not None or num_steps is not None

@@ -266,6 +266,8 @@ class RPEnv:
         self._graph_fresh = True
         self._static_version = getattr(self, '_static_version', 0) + 1
         self._table_key = None
+        self._max_step_buf = None
+        self._destroy_buf = None
 
     def _stream(self):
         return _cabi.stream_ptr(self.device)
@@ -620,10 +622,103 @@ class RPEnv:
             tours.append(tour_set)
         return tours
 
+    # ------------------------------------------------------------------ dense solution format
+    def _lists_to_dense(self, sol: List[List]) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        """Nested lists (instances x samples x tours, the reference's format, env.py:578-581) -> dense arrays
+        ``tours (n_sol, T, L) int16`` (customers, zero padded) and ``kind (n_sol, T) uint8`` (1 complete = list starts
+        and ends at the depot, 2 partial, 0 none); singleton tours are skipped like the reference skips them."""
+        L = self.state.L
+        flat = [smp for inst_sol in sol for smp in inst_sol]
+        T = max(1, max(sum(1 for t in smp if len(t) > 1) for smp in flat))
+        tours = np.zeros((len(flat), T, L), dtype=np.int16)
+        kind = np.zeros((len(flat), T), dtype=np.uint8)
+        for j, smp in enumerate(flat):
+            t_idx = 0
+            for tour in smp:
+                l = len(tour)
+                if l <= 1:
+                    continue
+                if tour[0] == tour[-1] == 0:
+                    body, kd = tour[1:-1], 1
+                else:
+                    body, kd = tour, 2
+                    if 0 in body:
+                        raise ValueError("a partial tour must not contain the depot")
+                if len(body) > L:
+                    raise RuntimeError(f"tour with {len(body)} customers exceeds the tour buffer ({L})")
+                tours[j, t_idx, :len(body)] = body
+                kind[j, t_idx] = kd
+                t_idx += 1
+        return torch.from_numpy(tours), torch.from_numpy(kind), T
+
+    def _import_dense(self, tours: torch.Tensor, kind: torch.Tensor, src_index: Optional[torch.Tensor],
+                      total_in: Optional[torch.Tensor]) -> RPObs:
+        """import_sol on the device (jampr_env_import_tours + jampr_env_import_finish)."""
+        st = self.state
+        dev = self.device
+        tours = tours.to(dev, torch.int16).contiguous()
+        kind = kind.to(dev, torch.uint8).contiguous()
+        n_sol, T, Lt = tours.shape
+        if src_index is not None:
+            src_index = src_index.to(dev, torch.int32).contiguous()
+            assert src_index.numel() == self.bs
+        else:
+            assert n_sol == self.bs
+        if total_in is not None:
+            total_in = total_in.to(dev, torch.float32).contiguous()
+            assert total_in.numel() == self.bs
+        if self._max_step_buf is None:
+            self._max_step_buf = torch.zeros(1, dtype=torch.int32, device=dev)
+        _cabi.check(self._lib.jampr_env_import_tours(self._dims, self._inst, st.struct(), _cabi.ptr(tours), _cabi.ptr(kind),
+                                                     T, Lt, _cabi.ptr(src_index), _cabi.ptr(total_in), self._stream()),
+                    "jampr_env_import_tours")
+        _cabi.check(self._lib.jampr_env_import_finish(self._dims, self._inst, st.struct(), _cabi.ptr(self._max_step_buf),
+                                                      self._stream()), "jampr_env_import_finish")
+        # the reference rebuilds the tour graph with the PREVIOUS episode's step counter (env.py:700 before
+        # :704, SURVEY.md A.6): same rule, same stale value
+        prev_step = self._step if self._step is not None else 0
+        self._graph_fresh = (prev_step <= st.K + 1) or (prev_step % self.tour_graph_update_step == 0)
+        self._has_instance = True
+        self._is_reset = True
+        self._done = False
+        self._step = int(self._max_step_buf.item())
+        self._raise_status()
+        return self._get_observation()
+
     def import_sol(self, sol: List[List], cost: Optional[List] = None) -> RPObs:
-        """Import partial solutions (env.py:575-706).  The list parsing stays on the host like the
-        reference's; state arrays are assembled in numpy, uploaded once, and the device derives visited
-        flags / tour links / the first observation (jampr_env_import_finish)."""
+        """Import partial solutions (env.py:575-706).  The nested lists are flattened to dense tour arrays on the host
+        (no per-node work), everything else — tour buffers, vehicle slots, capacity / clock of the partial tours,
+        recomputed totals (env.py:708-718), visited flags, tour links, first observation — runs on the device."""
+        assert self.inference, "Can only import solutions in inference mode."
+        assert self.state is not None, "import_sol needs a previous reset() (reference reuses its buffers)"
+        P = self._num_samples
+        I = self.n_inst
+        assert len(sol) == I
+        n_samples = np.array([len(s) for s in sol])
+        assert np.all(n_samples == n_samples[0])
+        n_samples = int(n_samples[0])
+        if self.pomo:
+            assert P == n_samples, (f"imported solutions for POMO must include num_samples samples, "
+                                    f"but got {n_samples} != {P}")
+        else:
+            assert P % n_samples == 0
+        fact = P // n_samples
+        tours, kind, _ = self._lists_to_dense(sol)
+        if int(kind.ne(0).sum(-1).max()) > self.state.K_max:
+            raise RuntimeError("Number of tours of provided solution is larger than max_num_vehicles!")
+        src = None
+        if fact > 1:                    # _expand_sample_dimension (env.py:1204-1219)
+            src = torch.arange(I * n_samples, dtype=torch.int32).repeat_interleave(fact)
+        total_in = None
+        if cost is not None:
+            c = torch.as_tensor(np.asarray(cost, dtype=np.float32).reshape(-1))
+            total_in = c if c.numel() == self.bs else c.repeat_interleave(fact)[: self.bs]
+        return self._import_dense(tours, kind, src, total_in)
+
+    def _import_sol_host(self, sol: List[List], cost: Optional[List] = None) -> RPObs:
+        """Round-1 implementation of import_sol, kept as the CHECKER of the device path (tests compare the state arrays
+        of both bit for bit): the reference's triple loop (env.py:612-690) in numpy on the host, state arrays uploaded
+        once, then jampr_env_import_finish."""
         assert self.inference, "Can only import solutions in inference mode."
         assert self.state is not None, "import_sol needs a previous reset() (reference reuses its buffers)"
         P = self._num_samples
@@ -716,6 +811,9 @@ class RPEnv:
             st[name].copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(self.device))
         st["row_last"].zero_()
         st["cost"].zero_()
+        st["status"].zero_()
+        for name in ("visited", "pred", "succ"):
+            st[name].zero_()
         max_step = torch.zeros(1, dtype=torch.int32, device=self.device)
         _cabi.check(self._lib.jampr_env_import_finish(self._dims, self._inst, st.struct(), _cabi.ptr(max_step),
                                                       self._stream()), "jampr_env_import_finish")
@@ -730,5 +828,67 @@ class RPEnv:
         self._raise_status()
         return self._get_observation()
 
-    def destruct(self, **kwargs):
-        raise NotImplementedError
+    def destruct(self, num_best: int = 2, num_other: int = 3, num_partial: Optional[int] = None,
+                 rm_partial_mode: str = "random", rm_complete_mode: str = "random",
+                 frac_rm_nodes_from_partial: float = 0.5, frac_rm_complete_routes: float = 0.15,
+                 seed: int = 1, iteration: int = 0, incumbent_plan: Optional[torch.Tensor] = None,
+                 incumbent_cost: Optional[torch.Tensor] = None, sources: Optional[torch.Tensor] = None,
+                 **kwargs) -> RPObs:
+        """Tensor-native select -> bootstrap -> destroy -> import on the finished episode held by this env: the
+        operator the reference left as a stub (env.py:720-723), for its ``random_from_route`` destruction
+        (destructor.py:86-205) and the selection / bootstrap of lns.py:296-313 with ``mode="random"``.
+
+        Per instance the ``num_best`` cheapest samples and ``num_other`` random others are selected (export_sol,
+        env.py:484-497, 546-552); if ``incumbent_plan (I, K_max, L)`` / ``incumbent_cost (I,)`` are given and the
+        incumbent is not among them it replaces the most expensive one (lns.py:209-222); the selection is repeated
+        to ``num_samples`` rollouts, each is mutilated with its own random stream and imported.  ``sources``
+        ``(I, n_sel, K_max, L)`` replaces the selection (sharded LNS: the globally selected tour buffers).
+        Nothing leaves the device except the new step counter.  Returns the first observation of the repair episode."""
+        assert self.inference and self.state is not None
+        st = self.state
+        I, P, R, L = self.n_inst, self._num_samples, st.K_max, st.L
+        n_sel = num_best + num_other
+        if sources is None:
+            assert P > n_sel and P % n_sel == 0, "num_samples must be a multiple of num_best + num_other (lns.py:307)"
+            plan = st["plan"].view(I, P, R, L)
+            total = st["total"].view(I, P)
+            order = total.sort(dim=-1, stable=True).indices
+            idx = order[:, :num_best]
+            if num_other > 0:
+                w = torch.ones(I, P - num_best, device=self.device)
+                rnd = torch.multinomial(w, num_other, replacement=False, generator=self._gen)
+                idx = torch.cat((idx, order[:, num_best:].gather(-1, rnd)), -1)
+            sources = plan.gather(1, idx[:, :, None, None].expand(-1, -1, R, L)).contiguous()
+            sel_cost = total.gather(-1, idx)
+            if incumbent_plan is not None:
+                inc = incumbent_cost.to(self.device, torch.float32).view(I, 1)
+                worst = sel_cost.argmax(-1)
+                absent = ~(sel_cost == inc).any(-1)
+                rows = torch.nonzero(absent).view(-1)
+                sources[rows, worst[rows]] = incumbent_plan.to(self.device, torch.int16)[rows]
+        else:
+            sources = sources.to(self.device, torch.int16).contiguous()
+            n_sel = sources.size(1)
+            assert P % n_sel == 0
+        # bootstrap (lns.py:304-310): the list of selected solutions repeated P / n_sel times
+        src_index = (torch.arange(P, device=self.device, dtype=torch.int32) % n_sel)[None, :] \
+            + (torch.arange(I, device=self.device, dtype=torch.int32) * n_sel)[:, None]
+        src_index = src_index.reshape(-1).contiguous()
+        prm = _cabi.Destroy()
+        prm.num_partial = int(self.max_concurrent_vehicles if num_partial is None else num_partial)
+        prm.rm_partial_mode = _cabi.RM_PARTIAL_MODES[rm_partial_mode]
+        prm.rm_complete_mode = _cabi.RM_COMPLETE_MODES[rm_complete_mode]
+        prm.frac_partial = float(frac_rm_nodes_from_partial)
+        prm.frac_complete = float(frac_rm_complete_routes)
+        prm.iteration = int(iteration)
+        prm.seed = int(seed)
+        if self._destroy_buf is None or self._destroy_buf[0].size(0) != self.bs:
+            self._destroy_buf = (torch.zeros(self.bs, R, L, dtype=torch.int16, device=self.device),
+                                 torch.zeros(self.bs, R, dtype=torch.uint8, device=self.device))
+        tours, kind = self._destroy_buf
+        import ctypes as _C
+        _cabi.check(self._lib.jampr_lns_destroy(self._dims, _cabi.ptr(sources.view(-1, R, L)), _cabi.ptr(src_index),
+                                                _C.byref(prm), _cabi.ptr(tours), _cabi.ptr(kind), self._stream()),
+                    "jampr_lns_destroy")
+        self._last_sources = sources
+        return self._import_dense(tours, kind, None, None)

@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard_list", "gather_best", "global_done_step"]
+__all__ = ["shard_bounds", "shard_list", "gather_best", "global_done_step", "lns_exchange"]
 
 
 def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
@@ -75,3 +75,31 @@ def global_done_step(local_done_step: int, device: torch.device, group: Optional
     t = torch.tensor([int(local_done_step)], dtype=torch.int32, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return int(t.item())
+
+
+def lns_exchange(total: torch.Tensor, plan: torch.Tensor, num_best: int, num_other: int, gen: torch.Generator,
+                 group: Optional[dist.ProcessGroup] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Selection step of the sharded LNS (BASELINE config 5; lib/lns/lns.py:296-313 with the sub-problems split over
+    the ranks): every rank contributes its ``num_best + num_other`` cheapest repaired solutions ``(total (P_r,), plan
+    (P_r, K_max, L))``; one all_gather of costs and one of tour buffers (~3.6 KB per candidate over NVLink); every rank
+    then keeps the globally cheapest ``num_best`` and ``num_other`` of the remaining candidates drawn with ``gen`` — a
+    CPU generator seeded identically on all ranks, so all ranks continue from the same sources without a broadcast.
+    Returns (costs (n_sel,), tour buffers (n_sel, K_max, L)).  Works on one rank (no collective) too."""
+    n_sel = num_best + num_other
+    order = total.sort(stable=True).indices[:n_sel]
+    costs, plans = total[order].contiguous(), plan[order].contiguous()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        cl = [torch.empty_like(costs) for _ in range(world)]
+        pb = plans.view(torch.uint8)            # int16 is not a collective dtype (NCCL / gloo): ship the bytes
+        pl = [torch.empty_like(pb) for _ in range(world)]
+        dist.all_gather(cl, costs, group=group)
+        dist.all_gather(pl, pb, group=group)
+        costs, plans = torch.cat(cl), torch.cat(pl).view(plans.dtype)
+    o = costs.sort(stable=True).indices
+    pick = o[:num_best]
+    if num_other > 0:
+        rest = o[num_best:]
+        perm = torch.randperm(rest.numel(), generator=gen)[:num_other].to(rest.device)
+        pick = torch.cat((pick, rest[perm]))
+    return costs[pick], plans[pick].clone()

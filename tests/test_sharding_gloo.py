@@ -60,3 +60,49 @@ def test_gather_best_gloo(tmp_path, world, n_total):
     mp.spawn(_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert os.path.exists(tmp_path / f"ok{r}.npy")
+
+
+def _lns_worker(rank, world, port, out_dir):
+    from jampr_plus_b200.sharding import lns_exchange
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, R, L, nb, no = 10, 4, 6, 2, 3
+        g = torch.Generator().manual_seed(100 + rank)                   # every rank repaired different sub-problems
+        total = torch.rand(P, generator=g)
+        plan = torch.randint(0, 50, (P, R, L), generator=g, dtype=torch.int16)
+        shared = torch.Generator().manual_seed(5)                       # same on all ranks
+        costs, src = lns_exchange(total, plan, nb, no, shared)
+        # reference: the union of all ranks' candidates, computed locally from the known seeds
+        allc, allp = [], []
+        for r in range(world):
+            gr = torch.Generator().manual_seed(100 + r)
+            t = torch.rand(P, generator=gr)
+            p = torch.randint(0, 50, (P, R, L), generator=gr, dtype=torch.int16)
+            o = t.sort(stable=True).indices[: nb + no]
+            allc.append(t[o])
+            allp.append(p[o])
+        allc, allp = torch.cat(allc), torch.cat(allp)
+        o = allc.sort(stable=True).indices
+        assert torch.equal(costs[:nb], allc[o[:nb]]) and torch.equal(src[:nb], allp[o[:nb]])
+        rest = o[nb:]
+        perm = torch.randperm(rest.numel(), generator=torch.Generator().manual_seed(5))[:no]
+        assert torch.equal(costs[nb:], allc[rest[perm]]) and torch.equal(src[nb:], allp[rest[perm]])
+        # every rank holds the same selection
+        mine = torch.cat((costs, src.float().view(-1)))
+        got = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(got, mine)
+        assert all(torch.equal(x, mine) for x in got)
+        np.save(os.path.join(out_dir, f"lns{rank}.npy"), np.array([1]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_lns_exchange_gloo(tmp_path, world):
+    """Selection step of the sharded LNS (config 5): candidates of all ranks, globally best + shared random others."""
+    port = _free_port()
+    mp.spawn(_lns_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert os.path.exists(tmp_path / f"lns{r}.npy")
