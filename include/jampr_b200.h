@@ -219,8 +219,8 @@ JAMPR_API int jampr_env_import_tours(const jampr_dims_t* d, const jampr_instance
  * native destruction operator circumventing expensive conversion to lists") — for lib/lns/destructor.py:86-205
  * `random_from_route`: per solution pick num_partial tours with more than one customer and mutilate them (random_nodes /
  * random_cut / const_cut), drop singleton tours, remove max(round(frac_complete * n), 1) of the remaining complete
- * tours (random or smallest).  Random numbers: jampr_uniform(seed, rollout, iteration * 8192 + draw), restated in
- * oracle/destroy_oracle.py.  src_plan (n_src, K_max, L) tour buffers; rollout b mutilates solution src_index[b];
+ * tours (random or smallest).  Random numbers: the counter-based generator of csrc/common.cuh keyed by (seed, rollout,
+ * iteration * 8192 + draw), restated in oracle/rng.py / oracle/destroy_oracle.py.  src_plan (n_src, K_max, L) tour buffers; rollout b mutilates solution src_index[b];
  * output in the dense format of jampr_env_import_tours with n_tours = K_max, tour_len = L (complete tours first). */
 typedef struct {
   int32_t  num_partial;        /* tours to mutilate per solution */
