@@ -57,27 +57,44 @@ def test_device_import_equals_host_import_on_reference_solution():
 
 
 def test_device_import_expand_and_given_costs():
-    """Non-POMO import with fewer samples than num_samples (env.py:1204-1219) and caller-supplied costs."""
-    from jampr_plus_b200 import RPEnv
+    """Non-POMO import with fewer samples than num_samples (_expand_sample_dimension, env.py:1204-1219) and
+    caller-supplied costs: solutions exported from a sampled episode, mutilated by the host Destructor."""
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.driver import rollout
+    from jampr_plus_b200.lns import Destructor
     from jampr_plus_b200.synth import sample_instances
+    from jampr_plus_b200.weights import random_state_dict
     inst = sample_instances(2, graph_size=30, seed=3)
-    sol = [[[[0, 1, 2, 3, 0], [4, 5], [6]], [[0, 7, 8, 0], [0, 9, 10, 11, 0], [12, 13, 14]]] for _ in inst]
-    outs = []
-    for path in ("device", "host"):
-        env = RPEnv(inference=True, device="cuda", max_concurrent_vehicles=2, k_nbh_frac=0.4, pomo=False, num_samples=6)
+    env = RPEnv(inference=True, device="cuda", max_concurrent_vehicles=2, k_nbh_frac=0.4, pomo=False, num_samples=6)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp32")
+    pol.load_state_dict(random_state_dict(0))
+    pol.set_decode_type("sampling")
+    pol.sampling_seed = 5
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
         env.load_data(inst)
         env.reset()
-        f = env.import_sol if path == "device" else env._import_sol_host
-        f(sol)
-        a = {k: env.state[k].clone() for k in STATE}
-        env.load_data(inst)
-        env.reset()
-        f(sol, cost=[1.0, 2.0, 3.0, 4.0])
-        outs.append((a, {k: env.state[k].clone() for k in STATE}))
+        rollout(pol, env)
+        sols, _ = env.export_sol(num_best=1, num_other=1, mode="random")
+        ds = Destructor(num_partial=2, seed=3)
+        sol = [ds.destruct(s) for s in sols]
+        outs = []
+        for path in ("device", "host"):
+            e = RPEnv(inference=True, device="cuda", max_concurrent_vehicles=2, k_nbh_frac=0.4, pomo=False, num_samples=6)
+            e.load_data(inst)
+            e.reset()
+            f = e.import_sol if path == "device" else e._import_sol_host
+            f(sol)
+            a = {k: e.state[k].clone() for k in STATE}
+            e.load_data(inst)
+            e.reset()
+            f(sol, cost=[1.0, 2.0, 3.0, 4.0])
+            outs.append((a, {k: e.state[k].clone() for k in STATE}))
     for k in STATE:
         assert torch.equal(outs[0][0][k], outs[1][0][k]), k
         assert torch.equal(outs[0][1][k], outs[1][1][k]), k
     assert outs[0][1]["total"].tolist() == [1.0] * 3 + [2.0] * 3 + [3.0] * 3 + [4.0] * 3
+    assert torch.equal(outs[0][0]["plan"][0], outs[0][0]["plan"][2]) and not torch.equal(outs[0][0]["plan"][0], outs[0][0]["plan"][3])
 
 
 @pytest.mark.parametrize("pmode,cmode,fp,fc", [("random", "random", 0.5, 0.15), ("random_nodes", "smallest", 0.0, 0.3),
