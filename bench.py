@@ -68,6 +68,7 @@ def parse():
                     help="instances per step of the CPU arm (x16 samples); 0 = max(1, ceil(12 / steps))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extras", default="all", help="comma list of strong,config3,fp32,bf16,gh1000,lns | all | none")
+    ap.add_argument("--lns-time", type=float, default=20.0, help="wall-clock budget of the LNS extra (BASELINE metric: 60)")
     ap.add_argument("--no-status-check", action="store_true", help="ablation builds only: skip the status-word assertion")
     return ap.parse_args()
 
@@ -504,6 +505,37 @@ def main():
             roof["secondary"] = env_roof
         par = parity_probe(dev, args.precision)
 
+    # ---- BASELINE config 4 (GH-1000 shape, weak scaling) and configs 1 / 5 (LNS; sharded sub-problems for N > 1): all ranks
+    del resident
+    torch.cuda.empty_cache()
+    if "gh1000" in extras_sel:
+        try:
+            from tools.bench_gh1000 import bench_gh1000
+            barrier()
+            r = bench_gh1000(dev, precision=args.precision, world=world)
+            if world > 1:
+                t = torch.tensor([r["seconds_per_episode"]], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                r["seconds_per_episode"] = float(t.item())
+                r["value"] = r["rollouts_per_gpu"] * world / r["seconds_per_episode"]
+                r["scaling"] = "weak"
+            extras["gh1000"] = r
+        except Exception as e:      # noqa: BLE001 - an extra must never take the headline line down
+            if world > 1:
+                raise
+            extras["gh1000"] = {"error": f"{type(e).__name__}: {e}"}
+    if "lns" in extras_sel:
+        try:
+            from tools.lns_solomon import bench_lns
+            barrier()
+            extras["lns"] = bench_lns(dev, precision=args.precision, time_limit=args.lns_time,
+                                      instance="c103.txt" if world == 1 else "r101.txt")
+        except Exception as e:      # noqa: BLE001
+            if world > 1:
+                raise
+            extras["lns"] = {"error": f"{type(e).__name__}: {e}"}
+    resident = {k: v.to(dev) for k, v in host.items()}
+
     # ---- other precisions on rank 0 (N = 1 runs only): same workload, resident arrays
     if rank == 0 and world == 1:
         for prec, n_i in (("fp32", 512), ("bf16", I)):
@@ -524,19 +556,6 @@ def main():
                             (" (the 1e-5 parity anchor, CUDA cores)" if prec == "fp32" else
                              " (reduced accuracy: not a supported product precision)")}
             del env_p, pol_p
-        if "gh1000" in extras_sel:
-            try:
-                from tools.bench_gh1000 import bench_gh1000
-                extras["gh1000"] = bench_gh1000(dev, precision=args.precision)
-            except Exception as e:      # noqa: BLE001 - an extra must never take the headline line down
-                extras["gh1000"] = {"error": f"{type(e).__name__}: {e}"}
-        if "lns" in extras_sel:
-            try:
-                from tools.lns_solomon import bench_lns
-                extras["lns"] = bench_lns(dev, precision=args.precision)
-            except Exception as e:      # noqa: BLE001
-                extras["lns"] = {"error": f"{type(e).__name__}: {e}"}
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

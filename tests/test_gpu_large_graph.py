@@ -125,3 +125,54 @@ def test_gehring_homberger_files():
     r1 = read_solomon(os.path.join(data, "R1_10_1.TXT"))
     with pytest.raises(AssertionError):
         env.load_data([r1])
+
+
+def test_c1_10_1_prefix_vs_oracle():
+    """BASELINE config 4 at its real size: the Gehring-Homberger file C1_10_1 (N = 1001, k = 51, K_max = 255, K6
+    overrides), 2 deterministic POMO samples, the first steps of the episode teacher-forced against the CPU oracle:
+    environment side bit-exact, node encoder / node embeddings / log-probabilities within the bars of the N = 301 test."""
+    import os
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.lns import read_solomon
+    from jampr_plus_b200.weights import random_state_dict
+    from oracle.env_oracle import OracleEnv
+    from oracle.policy_oracle import OraclePolicy, select_greedy
+    data = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+    c1 = read_solomon(os.path.join(data, "C1_10_1.TXT"))
+    kw = dict(max_concurrent_vehicles=3, k_nbh_frac=0.05, pomo=True, pomo_single_start_node=True, num_samples=2,
+              tour_graph_update_step=4)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    oenv = OracleEnv(**kw)
+    oenv.load([c1])
+    opol = OraclePolicy(random_state_dict(0))
+    env = RPEnv(inference=True, device="cuda", **kw)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp16")
+    pol.load_state_dict(random_state_dict(0))
+    pol.return_logp = True
+    env.load_data([c1], dist_mat=oenv.dist)
+    assert env.graph_size == 1001 and env.k_nbh_size == 51 and env.max_vehicle_number == 255
+    assert torch.equal(env._knn[:, 1:, :50].cpu().long(), oenv.knn[:, 1:, :50]), "kNN table at N = 1001"
+    obs = env.reset()
+    oenv.reset()
+    with warnings.catch_warnings(), torch.no_grad():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        for t in range(9):              # steps 1..5 refresh the tour graph (step <= K + 1), then every 4th step
+            nbh, mask = oenv.observe()
+            assert torch.equal(obs.nbh.cpu().long(), nbh), f"nbh step {t}"
+            assert torch.equal(obs.nbh_mask.cpu(), mask), f"mask step {t}"
+            assert env._graph_fresh == oenv.graph_fresh, f"graph refresh rule step {t}"
+            pol(obs)
+            tour_emb, node_emb = opol.tour_encode(oenv)
+            lo = opol.decode(tour_emb, node_emb, nbh, mask)
+            if t == 0:
+                assert (env._static_emb.cpu() - opol.static_emb).abs().max() <= EMB_ATOL, "node encoder (static_emb)"
+            assert (env.state["ne"].cpu() - node_emb).abs().max() <= EMB_ATOL, f"node_emb step {t}"
+            lp = pol.log_probs(env).cpu()
+            fin = torch.isfinite(lo)
+            assert torch.equal(fin, torch.isfinite(lp))
+            assert (lp[fin] - lo[fin]).abs().max() <= LOGP_ATOL, f"log-probs step {t}"
+            act, _ = select_greedy(lo, nbh)
+            obs, cost, done, _ = env.step(act)
+            co, _ = oenv.step(act)
+            assert torch.equal(cost.cpu(), co), f"cost step {t}"
+    assert torch.equal(env.tour_plan.cpu(), oenv.plan)

@@ -18,6 +18,48 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def bench_gh1000(dev="cuda", precision="fp16", instances=60, samples=4, reps=2, world=1):
+    """BASELINE config 4 shape on one GPU (every rank of a multi-GPU run executes this on its own batch: weak scaling);
+    returns the dict bench.py prints under extras.gh1000."""
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.driver import rollout
+    from jampr_plus_b200.synth import sample_instances
+    from jampr_plus_b200.weights import random_state_dict
+    warnings.simplefilter("ignore")
+    torch.cuda.reset_peak_memory_stats(dev)
+    base = torch.cuda.memory_allocated(dev)
+    # Gehring-Homberger 1000-customer instances allow 250 vehicles (K_max = 255, step cap N + K_max + 1 = 1257)
+    inst = [x._replace(max_vehicle_number=250) for x in sample_instances(instances, graph_size=1000, seed=9)]
+    kw = dict(max_concurrent_vehicles=3, k_nbh_frac=0.05, pomo=True, num_samples=samples, tour_graph_update_step=4)
+    env = RPEnv(inference=True, device=dev, **kw)
+    env.seed(1)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device=dev, precision=precision)
+    pol.load_state_dict(random_state_dict(0))
+    times = []
+    for it in range(1 + reps):
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env.load_data(inst)
+        pol.reset_static()
+        env.reset()
+        total, info = rollout(pol, env)
+        cost, idx, plan = env.gather_best()
+        cost = cost.cpu()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        times.append(e0.elapsed_time(e1) * 1e-3)
+    sec = min(times[1:])
+    return {"what": "BASELINE config 4 shape: 1000-customer instances (N = 1001, k = 51, K_max = %d, K6 overrides: "
+                    "k_nbh_frac 0.05, tour_graph_update_step 4), full-length greedy POMO episodes, layer-wise tcgen05 "
+                    "GNN path" % env.max_vehicle_number,
+            "instances_per_gpu": instances, "samples": samples, "rollouts_per_gpu": env.bs,
+            "episode_steps": info["done_step"] + 1, "seconds_per_episode": sec, "value": env.bs * world / sec,
+            "unit": "rollouts/s", "policy_steps_per_s": env.bs * world * (info["done_step"] + 1) / sec,
+            "peak_mem_gb_per_gpu": (torch.cuda.max_memory_allocated(dev) - base) / 2**30,
+            "mean_best_cost": float(cost.mean()), "precision": precision, "n_gpus": world}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--instances", type=int, default=32)

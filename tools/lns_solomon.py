@@ -99,6 +99,47 @@ def run_cpu(inst, args):
             "incumbent_env_cost": best_cost, "incumbent_tour_cost": best_tc}
 
 
+def bench_lns(dev="cuda", precision="fp16", time_limit=20.0, cpu_time_limit=10.0, instance="c103.txt", group=None):
+    """BASELINE configs 1 / 5 for bench.py (extras.lns): the all-device LNS loop (RPEnv.destruct: selection, bootstrap,
+    destruction and import on tour buffers; no local search, stand-in weights) on a Solomon instance for a wall-clock
+    budget; on several ranks the sub-problems are sharded (LNS.search_device docstring).  The CPU oracle port runs the
+    same loop for ``cpu_time_limit`` seconds beside it (rank 0, single-GPU runs only)."""
+    import torch.distributed as dist
+    from jampr_plus_b200 import Policy, RPEnv
+    from jampr_plus_b200.lns import LNS, read_solomon
+    from jampr_plus_b200.weights import random_state_dict
+    warnings.simplefilter("ignore")
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    inst = read_solomon(os.path.join(ROOT, "tests", "data", instance))
+    env = RPEnv(inference=True, device=dev, **ENV_KW)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device=dev, precision=precision)
+    pol.load_state_dict(random_state_dict(0))
+    pol.eval()
+    LNS(inst, pol, env, seed=1234, selection_mode="random").search_device(num_steps=3, group=group)      # warm-up
+    lns = LNS(inst, pol, env, seed=1234, selection_mode="random")
+    t0 = time.time()
+    plan, cost, true_cost = lns.search_device(time_limit=time_limit, group=group)
+    dt = time.time() - t0
+    out = {"what": f"LNS on Solomon {instance.split('.')[0]} (BASELINE config {'5' if world > 1 else '1'}): construct -> "
+                   "[select -> destroy -> import -> repair]* entirely on tour buffers on the device, 20 sub-problems per "
+                   "GPU and iteration, K1 overrides, NO local search (OR-tools absent), stand-in weights: cost levels are "
+                   "not comparable with published ones, iterations per budget are",
+           "instance": instance, "time_limit_s": time_limit, "seconds": dt, "iterations": lns.step,
+           "ms_per_iteration": 1e3 * dt / max(lns.step, 1), "sub_problems_per_iteration": ENV_KW["num_samples"] * world,
+           "incumbent_env_cost": cost, "incumbent_tour_cost": true_cost, "n_gpus": world,
+           "n_tours": int((plan[:, 0] > 0).sum())}
+    if world == 1 and cpu_time_limit > 0:
+        class A:
+            pass
+        a = A()
+        a.cpu_time_limit = cpu_time_limit
+        c = run_cpu(inst, a)
+        out["cpu_port"] = {"seconds": c["seconds"], "iterations": c["iterations"], "threads": c["threads"],
+                           "ms_per_iteration": 1e3 * c["seconds"] / max(c["iterations"], 1),
+                           "incumbent_env_cost": c["incumbent_env_cost"], "incumbent_tour_cost": c["incumbent_tour_cost"]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--instance", default=os.path.join(ROOT, "tests", "data", "c103.txt"))
