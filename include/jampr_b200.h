@@ -9,10 +9,9 @@
  * Conventions
  *  - Every pointer inside the structs is a DEVICE pointer owned by the caller (torch-allocated); the
  *    library allocates nothing persistent and never synchronises the stream.  It holds no state between calls
- *    except two debugging switches that are read ONCE from the process environment on first use and select between
- *    equivalent kernels (results within the documented tolerances either way): JAMPR_TC_VARIANT (1 = one-CTA-per-SM
- *    tiling of the fused policy step, 2 = two-CTA tiling with the fused decoder, default 3 = two-CTA tiling + split
- *    tcgen05 decoder) and JAMPR_NODE_ENCODER=fp32 (CUDA-core node encoder on the 16-bit precisions).
+ *    except one debugging switch that is read ONCE from the process environment on first use: JAMPR_NODE_ENCODER=fp32
+ *    (CUDA-core node encoder on the 16-bit precisions; results within the documented tolerances either way).  Kernel
+ *    variants of the policy step are selected per call through jampr_weights_t.tc_variant.
  *  - All calls enqueue work on `stream` (a cudaStream_t passed as void*) and return 0 on success,
  *    a negative JAMPR_E_* code for argument errors, or a positive cudaError_t for launch errors.
  *  - Data-dependent conditions the reference raises on are OR-ed into `status[rollout]`
@@ -158,8 +157,14 @@ typedef struct {
   const void*  blob_bf16;  /* 16-bit (bf16 or fp16, see precision) operands in UMMA tile order (packing.pack_tc), or NULL */
   int64_t      n_bf16;     /* elements of blob_bf16 */
   int32_t      precision;  /* JAMPR_PREC_* */
-  int32_t      reserved;
+  int32_t      tc_variant; /* kernel selection of the 16-bit path for graphs of up to 128 nodes: 0 = automatic (3 when the batch has
+                              at least JAMPR_SPLIT_MIN_ROLLOUTS rollouts, else 2), 1 = one-CTA-per-SM tiling with the decoder fused
+                              (csrc/policy_tc.cu), 2 = two-CTA tiling with the decoder fused per rollout (csrc/policy_tc2.cu),
+                              3 = two-CTA tiling + the tcgen05 decoder over 128 rollouts per CTA (csrc/decoder_tc.cu).  All
+                              variants meet the documented tolerances; 3 wins on large batches (weights read once per 128
+                              rollouts), 2 on small ones (no latency-bound GEMM chain in a single CTA). */
 } jampr_weights_t;
+#define JAMPR_SPLIT_MIN_ROLLOUTS 8192
 
 JAMPR_API int jampr_abi_version(void);
 

@@ -14,6 +14,7 @@ ABI_VERSION = 4
 ST_NO_FEASIBLE, ST_TOUR_OVERFLOW, ST_FLEET_EXHAUSTED, ST_NAN_LOGITS, ST_TW_COLLAPSE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLING = 0, 1
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
+SPLIT_MIN_ROLLOUTS = 8192
 CTL_N_ALLVIS, CTL_DONE_STEP, CTL_HOLD, CTL_LOCAL_DONE, CTL_FINAL_STEP, CTL_WORDS = 0, 1, 2, 3, 4, 8
 ERRORS = {-1: "bad argument", -2: "graph too large for the on-chip tile of this build", -3: "unsupported"}
 
@@ -42,7 +43,7 @@ class State(C.Structure):
 
 class Weights(C.Structure):
     _fields_ = [("blob", _p), ("n_floats", C.c_int64), ("blob_bf16", _p), ("n_bf16", C.c_int64),
-                ("precision", C.c_int32), ("reserved", C.c_int32)]
+                ("precision", C.c_int32), ("tc_variant", C.c_int32)]
 
 
 class Destroy(C.Structure):

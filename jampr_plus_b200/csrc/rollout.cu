@@ -24,17 +24,16 @@ int jampr_lg_tour_encoder(const jampr_dims_t*, const jampr_instances_t*, const j
                           int, cudaStream_t);
 #define JAMPR_TILE_NODES 128     // graphs up to this size run the single-tile kernels, larger ones the layer-wise path
 
-// Tensor-core policy step.  Default (variant 3): the two-CTAs-per-SM GNN kernel (policy_tc2.cu) in split mode followed
-// by the 128-rollouts-per-CTA tcgen05 decoder (decoder_tc.cu), when the caller supplied the hand-over buffers and the
-// shapes fit; variant 2: the same GNN kernel with the decoder fused per rollout; variant 1 (and graphs that do not fit
-// the two-CTA tiling): the one-CTA tiling (policy_tc.cu).  JAMPR_TC_VARIANT selects (A/B measurements, header).
+// Tensor-core policy step, variant per jampr_weights_t.tc_variant (include/jampr_b200.h): 3 = the two-CTAs-per-SM GNN
+// kernel (policy_tc2.cu) in split mode followed by the 128-rollouts-per-CTA tcgen05 decoder (decoder_tc.cu), when the
+// caller supplied the hand-over buffers and the shapes fit; 2 = the same GNN kernel with the decoder fused per rollout;
+// 1 (and graphs that do not fit the two-CTA tiling) = the one-CTA tiling (policy_tc.cu); 0 = 3 for large batches, else 2.
 static int policy_step_tc_any(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
                               const jampr_state_t* st, int fresh, int step_no, int decode_type, uint64_t seed,
                               const float* uniforms, int store_cache, cudaStream_t s) {
-  static const int variant = [] {
-    const char* e = getenv("JAMPR_TC_VARIANT");
-    return (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
-  }();
+  int variant = w->tc_variant;
+  if (variant <= 0 || variant > 3)
+    variant = ((int64_t)d->n_inst * d->n_samples >= JAMPR_SPLIT_MIN_ROLLOUTS) ? 3 : 2;
   if (variant >= 2) {
     const bool split = variant == 3 && st->ne16 && st->dq && st->dte && st->dqp && st->dgbar && st->dlp &&
                        jampr_decoder_tc_fits(d);

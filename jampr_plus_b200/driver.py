@@ -31,7 +31,7 @@ def _graph_key(policy, env, n):
     dims = tuple(int(getattr(env._dims, f)) for f, _ in env._dims._fields_)
     state = tuple(sorted((name, t.data_ptr()) for name, t in st.t.items()))
     return (inst, dims, state, policy._blob.data_ptr(), 0 if policy._blob_bf16 is None else policy._blob_bf16.data_ptr(),
-            policy._blob_version, policy.precision, int(env._step), int(env._graph_fresh), policy._decode_code(),
+            policy._blob_version, policy.precision, int(policy.tc_variant), int(env._step), int(env._graph_fresh), policy._decode_code(),
             int(policy.sampling_seed), int(n), int(st["ctl"].data_ptr()))
 
 

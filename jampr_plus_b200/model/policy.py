@@ -92,7 +92,8 @@ class Policy(nn.Module):
 
     Extra keywords (not in the reference): ``precision`` = ``"fp32"`` (CUDA-core path, the 1e-5 parity anchor) or
     ``"fp16"`` (tcgen05 tensor-core GEMMs on 16-bit operands with fp32 accumulation, epilogues and skip connections:
-    log-probabilities within 1e-3 relative of the reference).  ``"bf16"`` runs the same kernels on bf16 operands but
+    log-probabilities within 1e-3 relative of the reference); ``tc_variant`` selects among its equivalent kernel
+    organisations (0 = automatic by batch size, see include/jampr_b200.h).  ``"bf16"`` runs the same kernels on bf16 operands but
     misses that tolerance by an order of magnitude; it is refused unless ``allow_reduced_accuracy=True``."""
 
     def __init__(self,
@@ -107,6 +108,7 @@ class Policy(nn.Module):
                  device: Union[str, int, torch.device] = "cuda",
                  precision: str = "fp32",
                  allow_reduced_accuracy: bool = False,
+                 tc_variant: Optional[int] = None,
                  **kwargs):
         super().__init__()
         if (node_encoder_type, tour_encoder_type, decoder_type) != ("NodeEncoder", "TourEncoder", "AttnDecoder"):
@@ -128,6 +130,13 @@ class Policy(nn.Module):
         self.observation_space = observation_space
         self.embedding_dim = embedding_dim
         self.precision = precision
+        # kernel variant of the 16-bit policy step (include/jampr_b200.h, jampr_weights_t.tc_variant): 0 = automatic
+        if tc_variant is None:
+            import os
+            tc_variant = int(os.environ.get("JAMPR_TC_VARIANT", "0"))
+        if tc_variant not in (0, 1, 2, 3):
+            raise ValueError("tc_variant must be 0 (automatic), 1, 2 or 3")
+        self.tc_variant = tc_variant
         self._device = torch.device(device)
         self.node_feature_dim = observation_space["node_features"]
         self.tour_feature_dim = observation_space["tour_features"]
@@ -194,6 +203,7 @@ class Policy(nn.Module):
         w.blob_bf16 = _cabi.ptr(self._blob_bf16)
         w.n_bf16 = 0 if self._blob_bf16 is None else self._blob_bf16.numel()
         w.precision = {"fp32": _cabi.PREC_F32, "bf16": _cabi.PREC_BF16, "fp16": _cabi.PREC_F16}[self.precision]
+        w.tc_variant = int(self.tc_variant)
         return w
 
     def _decode_code(self) -> int:

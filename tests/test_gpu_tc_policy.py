@@ -34,12 +34,13 @@ def logp_tol(ref):
     return LOGP_RTOL * np.maximum(1.0, np.abs(ref))
 
 
-def _make(g, precision):
+def _make(g, precision, tc_variant=0):
     from jampr_plus_b200 import Policy, RPEnv
     from jampr_plus_b200.weights import random_state_dict
     env = RPEnv(inference=True, device="cuda", **env_args(g["env_kwargs"]))
     env.seed(1)
-    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision, allow_reduced_accuracy=True)
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision=precision, allow_reduced_accuracy=True,
+                 tc_variant=tc_variant)
     pol.load_state_dict(random_state_dict(int(g["policy_seed"])))
     pol.eval()
     pol.return_logp = True
@@ -58,11 +59,13 @@ def _sn(g):
     return None if sn is None else sn.to(torch.int32)
 
 
-@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("precision,variant", [("fp16", 2), ("fp16", 3), ("bf16", 3)])
 @pytest.mark.parametrize("name", CASES)
-def test_teacher_forced_tc(name, precision):
+def test_teacher_forced_tc(name, precision, variant):
+    """variant 2 = decoder fused per rollout (what small batches run), 3 = tcgen05 decoder over 128 rollouts (large
+    batches): both against the reference trace, same bars."""
     g = load_case(name)
-    env, pol = _make(g, precision)
+    env, pol = _make(g, precision, variant)
     envr, polr = _make(g, "fp32")
     obs, obr = env.reset(start_nodes=_sn(g)), envr.reset(start_nodes=_sn(g))
     T = g["trace_action"].shape[0]
@@ -111,14 +114,14 @@ def test_teacher_forced_tc(name, precision):
           f"differ, {n_decisive} decisive")
 
 
-@pytest.mark.parametrize("precision", ["fp16"])
+@pytest.mark.parametrize("precision,variant", [("fp16", 2), ("fp16", 3)])
 @pytest.mark.parametrize("name", ["g21_pomo", "g31_k2", "g51_upd2"])
-def test_fused_rollout_tc(name, precision):
+def test_fused_rollout_tc(name, precision, variant):
     """Free-running device loop on the tensor-core path: every rollout whose reference decisions are all decisive
     reproduces the reference tours; the step API and the fused loop agree bit for bit with each other."""
     from jampr_plus_b200.driver import rollout
     g = load_case(name)
-    env, pol = _make(g, precision)
+    env, pol = _make(g, precision, variant)
     pol.return_logp = False
     srt = np.sort(g["trace_logp"], -1)
     decided = ((srt[..., -1] - srt[..., -2]) > logp_tol(srt[..., -1]) + logp_tol(srt[..., -2])).all(0)
@@ -141,12 +144,13 @@ def test_fused_rollout_tc(name, precision):
     assert torch.equal(env.total_cost, total)
 
 
-def test_tc_sampling_uses_given_uniforms():
+@pytest.mark.parametrize("variant", [2, 3])
+def test_tc_sampling_uses_given_uniforms(variant):
     """Sampling decode on the tensor-core path: the action is the inverse-CDF pick of the kernel's own
     log-probabilities for the caller's uniforms (same rule as the fp32 path / oracle.select_inverse_cdf)."""
     from oracle.policy_oracle import select_inverse_cdf
     g = load_case("g51_sampling")
-    env, pol = _make(g, "fp16")
+    env, pol = _make(g, "fp16", variant)
     pol.set_decode_type("sampling")
     obs = env.reset()
     gen = torch.Generator().manual_seed(11)
@@ -236,14 +240,14 @@ def test_tc_rollout_is_deterministic_under_load(precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
-def test_seeded_sampling_replays_on_cpu(precision):
+def test_seeded_sampling_replays_on_cpu(precision, variant=3):
     """Sampling without caller-supplied uniforms: the kernel draws from jampr_uniform(seed, rollout, step)
     (csrc/common.cuh); oracle/rng.py is its CPU twin, so the episode can be replayed: the inverse-CDF pick of the
     kernel's own log-probabilities at the twin's uniforms must equal the kernel's action, every step."""
     from oracle.policy_oracle import select_inverse_cdf
     from oracle.rng import uniforms
     g = load_case("g51_sampling")
-    env, pol = _make(g, precision)
+    env, pol = _make(g, precision, variant)
     pol.set_decode_type("sampling")
     pol.sampling_seed = 987654321
     obs = env.reset()
