@@ -473,3 +473,34 @@ def test_sharded_rollout_reproduces_union_batch_totals(name, precision):
     np.testing.assert_allclose(t0.cpu().numpy(), total_u[: cut * P].cpu().numpy(), rtol=FINAL_COST_RTOL, atol=0)
     assert info0["done_step"] == final
     print(f"{name}: shard finishing steps {locals_}, union {final}")
+
+
+def test_export_sol_against_reference_lists():
+    """RPEnv.export_sol (env.py:465-573) against lists exported by the unmodified reference from the same final state
+    (tests/golden/export_sol.json, tests/golden/make_export_golden.py): cheapest samples per instance, similarity
+    selection, singleton tours for unvisited customers, cost lists — exact."""
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "export_sol.json")))
+    for case, calls in ref.items():
+        g = load_case(case)
+        env, _ = _make(g)
+        env.reset(start_nodes=_sn(g))
+        env.state["plan"].copy_(torch.from_numpy(g["final_tour_plan"]).cuda())
+        env.state["total"].copy_(torch.from_numpy(g["final_total_cost"]).cuda())
+        for c in calls:
+            sols, costs = env.export_sol(num_best=c["num_best"], num_other=c["num_other"], mode=c["mode"])
+            assert sols == c["solutions"], (case, c["mode"])
+            assert np.array_equal(np.asarray(costs, dtype=np.float32), np.asarray(c["costs"], dtype=np.float32))
+
+
+def test_static_node_embedding_against_reference():
+    """Node encoder output (node_encoder.py:128-155) of the first g101_pomo instance against the reference's
+    `static_node_emb`: fp32 path to 3e-5, fp16 tensor-core path (tcgen05 GraphConv tiles) to the 16-bit operand bar."""
+    g = load_case("g101_pomo")
+    for prec, tol in (("fp32", 3e-5), ("fp16", 4e-3)):
+        env, pol = _make(g, precision=prec)
+        obs = env.reset(start_nodes=_sn(g))
+        pol(obs)
+        err = float((env._static_emb[0].cpu() - torch.from_numpy(g["static_node_emb0"])).abs().max())
+        assert err <= tol, (prec, err)
