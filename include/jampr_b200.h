@@ -239,6 +239,16 @@ typedef struct {
 JAMPR_API int jampr_lns_destroy(const jampr_dims_t* d, const int16_t* src_plan, const int32_t* src_index,
                       const jampr_destroy_t* prm, int16_t* tours, uint8_t* kind, void* stream);
 
+/* Local search on tour buffers: the stand-in for the reference's OR-tools guided local search (lib/lns/gort.py:129-290,
+ * lib/utils/or_utils.py:10-171; OR-tools is neither installed nor pinned).  Best-improvement descent over relocate and
+ * 2-opt* moves, every move evaluated with the environment's own feasibility arithmetic (env.py:981-990, 1081-1131); at most
+ * max_iters moves per solution.  plans (n_solutions, K_max, L) is improved in place; inst_of (n_solutions) names the instance
+ * of each solution (NULL = solution / n_samples); cost_out (n_solutions) = batch-independent cost of the served tours (travel +
+ * waiting + service incl. return legs, normalised units; unserved customers are not touched and not charged here);
+ * moves_out (n_solutions) = moves applied.  Deterministic; restated in oracle/ls_oracle.py. */
+JAMPR_API int jampr_local_search(const jampr_dims_t* d, const jampr_instances_t* inst, int16_t* plans, int32_t n_solutions,
+                       const int32_t* inst_of, int32_t max_iters, float* cost_out, int32_t* moves_out, void* stream);
+
 /* Policy.forward for one step (policy.py:120-227; tour_encoder.py:159-243; attn_decoder.py:62-98):
  * tour-graph GNN (or cached embedding), tour embeddings, pointer attention, masked log-softmax,
  * greedy argmax or inverse-CDF sampling.  graph_fresh: 1 = rebuild the tour-graph embedding,

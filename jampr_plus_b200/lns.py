@@ -121,7 +121,7 @@ class LNS:
 
     def __init__(self, instance: RPInstance, policy, env, num_best: int = 2, num_other: int = 3,
                  add_best: bool = True, destructor: Optional[Destructor] = None, seed: int = 1234,
-                 use_graph: bool = True, selection_mode: str = "similarity"):
+                 use_graph: bool = True, selection_mode: str = "similarity", ls_step: int = 0, ls_iters: int = 200):
         assert env.inference and env.pomo, "LNS construction uses POMO inference (search/default.yaml: pomo_inference)"
         P = env.num_samples
         assert P % (num_best + num_other) == 0, "num_samples must be a multiple of num_best + num_other (lns.py:307)"
@@ -129,6 +129,9 @@ class LNS:
         self.num_best, self.num_other, self.add_best = num_best, num_other, add_best
         self.ds = destructor or Destructor(num_partial=env.max_concurrent_vehicles, seed=seed)
         self.use_graph = use_graph
+        # the reference runs OR-tools' guided local search every ls_step iterations (search/default.yaml ls_step,
+        # lns.py `_local_search`); here: the device local search (RPEnv.local_search), 0 = off
+        self.ls_step, self.ls_iters = int(ls_step), int(ls_iters)
         self.selection_mode = selection_mode          # config_lns/search/default.yaml: "similarity"
         self.horizon = float(instance.org_service_horizon)
         self.best_solution, self.best_cost, self.best_true_cost, self.best_step = None, float("inf"), float("inf"), -1
@@ -149,6 +152,11 @@ class LNS:
         else:
             env.import_sol([partial])
         rollout(pol, env, graph=self.use_graph and partial is None)
+        if self.ls_step > 0:
+            if self.step % self.ls_step == 0:
+                env.local_search(self.ls_iters)
+            else:
+                env.state["total"].copy_(env.true_cost())
         true = env.true_cost() * self.horizon
         sols, costs = env.export_sol(self.num_best, self.num_other, mode=self.selection_mode)
         # recover which samples were exported to attach their batch-independent cost
@@ -198,6 +206,8 @@ class LNS:
         env.load_data([self.inst])
         env.reset()
         rollout(pol, env, graph=self.use_graph)
+        if self.ls_step > 0:
+            env.local_search(self.ls_iters)
         kw = dict(num_best=self.num_best, num_other=self.num_other, num_partial=ds.num_partial,
                   rm_partial_mode=ds.rm_partial_mode, rm_complete_mode=ds.rm_complete_mode,
                   frac_rm_nodes_from_partial=ds.frac_p, frac_rm_complete_routes=ds.frac_c,
@@ -257,6 +267,10 @@ class LNS:
                 env.destruct(iteration=self.step, incumbent_plan=inc_plan if self.add_best else None,
                              incumbent_cost=inc_cost, **kw)
             rollout(pol, env, graph=self.use_graph)
+            if self.ls_step > 0 and self.step % self.ls_step == 0:
+                env.local_search(self.ls_iters)
+            elif self.ls_step > 0:
+                env.state["total"].copy_(env.true_cost())      # one cost scale for improved and untouched solutions
             incumbent_update()
             sync_incumbent()
             slowest = max(slowest, time.time() - ts)

@@ -828,6 +828,23 @@ class RPEnv:
         self._raise_status()
         return self._get_observation()
 
+    def local_search(self, max_iters: int = 200, update_totals: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Improve the finished solutions held by this env (tour buffers of all rollouts) by the device local search
+        (relocate / 2-opt*, csrc/local_search.cu) — the stand-in for the reference's OR-tools step (lns.py `_local_search`,
+        gort.py:129-290).  With ``update_totals`` the reported total of every rollout becomes the batch-independent cost
+        of its solution (served tours + 2 * time_to_depot per unserved customer), so that improved and untouched
+        solutions are compared on one scale.  Returns (cost of the served tours (bs,), moves applied (bs,))."""
+        assert self.state is not None
+        st = self.state
+        cost = torch.empty(self.bs, dtype=torch.float32, device=self.device)
+        moves = torch.empty(self.bs, dtype=torch.int32, device=self.device)
+        _cabi.check(self._lib.jampr_local_search(self._dims, self._inst, _cabi.ptr(st["plan"]), self.bs, None,
+                                                 int(max_iters), _cabi.ptr(cost), _cabi.ptr(moves), self._stream()),
+                    "jampr_local_search")
+        if update_totals:
+            st["total"].copy_(self.true_cost())
+        return cost, moves
+
     def destruct(self, num_best: int = 2, num_other: int = 3, num_partial: Optional[int] = None,
                  rm_partial_mode: str = "random", rm_complete_mode: str = "random",
                  frac_rm_nodes_from_partial: float = 0.5, frac_rm_complete_routes: float = 0.15,
