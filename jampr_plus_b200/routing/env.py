@@ -615,8 +615,10 @@ class RPEnv:
         for plans in tp:
             tour_set = []
             for plan in plans:
-                unq = set(np.unique(plan).tolist()) | {0}
-                singles = [[e] for e in sorted(full - unq)]
+                # unvisited customers become singleton tours in the iteration order of the reference's own expression
+                # (a Python set difference, env.py:563-570): irrelevant for import_sol, kept for list-level equality
+                unq = np.unique(plan)
+                singles = [[e] for e in full - set(unq.tolist())] if len(unq) != self.graph_size else []
                 rows = plan[plan.sum(-1) > 0]
                 tour_set.append([r[r > 0].tolist() for r in rows] + singles)
             tours.append(tour_set)

@@ -488,10 +488,22 @@ def test_export_sol_against_reference_lists():
         env.reset(start_nodes=_sn(g))
         env.state["plan"].copy_(torch.from_numpy(g["final_tour_plan"]).cuda())
         env.state["total"].copy_(torch.from_numpy(g["final_total_cost"]).cuda())
+        P = env.num_samples
+        st = env.state
+        every = env._sol_to_list(st["plan"].view(-1, P, st.K_max, st.L))
+        totals = st["total"].view(-1, P).cpu().numpy()
         for c in calls:
             sols, costs = env.export_sol(num_best=c["num_best"], num_other=c["num_other"], mode=c["mode"])
-            assert sols == c["solutions"], (case, c["mode"])
             assert np.array_equal(np.asarray(costs, dtype=np.float32), np.asarray(c["costs"], dtype=np.float32))
+            for i, (mine, ref) in enumerate(zip(sols, c["solutions"])):
+                for k, (m, r) in enumerate(zip(mine, ref)):
+                    if m == r:
+                        continue
+                    # the reference orders by an UNSTABLE torch.sort (env.py:478): samples of exactly equal cost may be
+                    # exported in either order — then both must be samples of this instance with that very cost
+                    cst = np.float32(c["costs"][i][k])
+                    tied = [every[i][q] for q in range(P) if totals[i, q] == cst]
+                    assert len(tied) > 1 and m in tied and r in tied, (case, c["mode"], i, k)
 
 
 def test_static_node_embedding_against_reference():
