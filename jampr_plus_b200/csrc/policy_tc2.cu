@@ -763,8 +763,6 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       if (r < N) {
         const float4* bo = reinterpret_cast<const float4*>(w + OFF_TE_OUT_B + col0);
         float4* gdst = a.store_cache ? reinterpret_cast<float4*>(st.ne + ((size_t)b * N + r) * 256 + col0) : nullptr;
-        uint4* g16 = SPLIT ? reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st.ne16) + (((size_t)b * N + r) * 256 + col0) * 2)
-                             : nullptr;      // split decoder: the 16-bit rows also go to HBM (decoder_tc.cu gathers them)
         uint8_t* dst = s_ne16 + (size_t)r * NE16_STRIDE + col0 * 2;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -777,7 +775,6 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
           const uint4 pk = make_uint4(as_u32(Elem<T>::from2(va.x, va.y)), as_u32(Elem<T>::from2(va.z, va.w)),
                                       as_u32(Elem<T>::from2(vb.x, vb.y)), as_u32(Elem<T>::from2(vb.z, vb.w)));
           *reinterpret_cast<uint4*>(dst + i * 16) = pk;
-          if (g16) g16[i] = pk;
           if (gdst) { gdst[2 * i] = va; gdst[2 * i + 1] = vb; }
         }
       }
@@ -811,6 +808,14 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   if (fresh && warp == 0) {
     tc_fence_after();
     tmem_dealloc(*tmem_slot, 256);
+  }
+  if (SPLIT && fresh && warp == 1) {
+    // split decoder: the parked 16-bit rows also go to HBM (decoder_tc.cu gathers the candidate rows from there), one
+    // 512-byte bulk copy per row by the copy engine while the CTA computes the column statistics below
+    fence_proxy_async();
+    uint8_t* g = reinterpret_cast<uint8_t*>(st.ne16) + (size_t)b * N * 512;
+    for (int rr = lane; rr < N; rr += 32) bulk_s2g(g + (size_t)rr * 512, s_ne16 + (size_t)rr * NE16_STRIDE, 512u);
+    bulk_commit();
   }
 
   // ---------------------------------------------------------------- decoder
@@ -875,7 +880,18 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       for (int t = 0; t < K; ++t) st.dte[((size_t)b * 4 + t) * 256 + tid] = s_te[t * 256 + tid];
     }
   }
-  if (SPLIT) return;
+  if (SPLIT) {
+    if (fresh && warp == 1) bulk_wait_all();       // the copy engine has read the parked rows: shared memory may go
+#ifdef JAMPR_TIMELINE
+    if (tid == 0) {
+      s_tl[23] = (uint32_t)clock64();
+      for (int q = 24; q <= 32; ++q) s_tl[q] = s_tl[23];
+      if ((b & 63) == 0 && (b >> 6) < 1024)
+        for (int q = 0; q < TL_N; ++q) g_timeline[b >> 6][q] = s_tl[q];
+    }
+#endif
+    return;
+  }
   __syncthreads();
   TL(23);
   // (c) ctxt = ctxt_proj(query)

@@ -32,12 +32,16 @@ def main(n_inst=4096, mhz=1965.0):
     lib = _cabi.load_library()
     if not hasattr(lib, "jampr_debug_timeline"):
         raise SystemExit("library was not built with -DJAMPR_TIMELINE")
-    arr = instances_to_arrays(sample_instances(n_inst, graph_size=100, seed=1234))
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                             "workload_all_1_low_4096.npz"))
+    arr = {k: z[k][:n_inst] for k in z.files if z[k].ndim > 0}
     dev = {k: torch.from_numpy(np.ascontiguousarray(arr[k])).to(torch.float32).cuda()
            for k in ("coords", "demands", "tw", "service_time", "org_service_horizon")}
     env = RPEnv(max_concurrent_vehicles=3, k_nbh_frac=0.25, pomo=True, num_samples=16, inference=True, device="cuda")
     env.seed(1235)
-    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp16")
+    pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp16",
+                 tc_variant=int(sys.argv[1]) if len(sys.argv) > 1 else 0)
     pol.load_state_dict(random_state_dict(0))
     pol.eval()
     with warnings.catch_warnings():
