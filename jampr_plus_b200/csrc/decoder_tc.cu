@@ -26,6 +26,7 @@
 #define DT_WARPS (DT_THREADS / 32)
 #define DT_M 128
 #define DT_BATCH 8             // node-embedding rows in flight per lane in the per-rollout passes
+#define DT_BATCH3 16           // same in the logit pass, which keeps few other registers live
 #define DT_ITEMS 32            // B tiles consumed: 8 (stage A) + 4 (B) + 16 (D) + 4 (E)
 
 struct DtArgs {
@@ -157,10 +158,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), b_addr = smem_u32(sB);
   const uint32_t idesc256 = umma_idesc(128, 256, Elem<T>::fmt), idesc64 = umma_idesc(128, 64, Elem<T>::fmt);
 
-  // A tile from a row-major fp32 matrix in HBM: thread = (row tid / 4, 16-column group tid % 4)
-  auto fill_from_global = [&](const float* src, size_t row_stride, int col0) {
+  // A tile from a row-major fp32 matrix in HBM: thread = (row tid / 4, 16-column group tid % 4).  Two halves: the loads
+  // of the NEXT item are issued before the wait for the current item's MMAs, the tile is written after it
+  auto load_global = [&](float (&v)[16], const float* src, size_t row_stride, int col0) {
     const int r = tid >> 2, g = tid & 3;
-    float v[16];
     if (b0 + r < bs) {
       const float4* p = reinterpret_cast<const float4*>(src + (size_t)(b0 + r) * row_stride + col0 + g * 16);
 #pragma unroll
@@ -172,8 +173,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = 0.0f;
     }
-    write_a16<T>(sAhi, sAlo, r, g, v);
   };
+  auto store_tile = [&](const float (&v)[16]) { write_a16<T>(sAhi, sAlo, tid >> 2, tid & 3, v); };
   // A tile from 64 accumulator columns in TMEM: warp = (lane quarter, 16-column group)
   auto fill_from_tmem = [&](uint32_t col0) {
     uint32_t raw[16];
@@ -200,14 +201,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       }
     }
   };
-  // one item: A tile is filled; issue the next B load, wait for this one, 12 MMAs (4 K steps x hi*hi, lo*hi, hi*lo)
-  auto run_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first) {
+  // one item, first half: the A tile is filled; issue the next B load, wait for this one, 12 MMAs (4 K steps x hi*hi,
+  // lo*hi, hi*lo), commit.  Second half: every thread waits for the MMAs (A tile and accumulator free / valid).
+  auto issue_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first) {
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      if (i + 1 < DT_ITEMS) issue_b(i + 1);          // its buffer was last read by item i - 1, complete (waited below)
+      if (i + 1 < DT_ITEMS) issue_b(i + 1);          // its buffer was last read by item i - 1, complete (waited)
       mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       const uint32_t bh = b_addr + (uint32_t)(i & 1) * 65536u, bl = bh + 32768u;
@@ -221,15 +223,27 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       }
       umma_commit(bar_mma);
     }
-    mbar_wait(bar_mma, (uint32_t)(i & 1));            // every thread: the A tile and the accumulator are free / valid
+  };
+  auto wait_item = [&](int i) {
+    mbar_wait(bar_mma, (uint32_t)(i & 1));
     tc_fence_after();
+  };
+  auto run_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first) {
+    issue_item(i, d_col, idesc, first);
+    wait_item(i);
   };
 
   // ================================================================ stage A: ctxt (TMEM columns 0..255)
+  {
+    float v[16];
+    load_global(v, st.dq, 512, 0);
 #pragma unroll 1
-  for (int kb = 0; kb < 8; ++kb) {
-    fill_from_global(st.dq, 512, kb * 64);
-    run_item(kb, 0u, idesc256, kb == 0);
+    for (int kb = 0; kb < 8; ++kb) {
+      store_tile(v);
+      issue_item(kb, 0u, idesc256, kb == 0);
+      if (kb + 1 < 8) load_global(v, st.dq, 512, (kb + 1) * 64);
+      wait_item(kb);
+    }
   }
   // ================================================================ stage B: qp_h (TMEM columns 256..511) -> st.dqp
 #pragma unroll 1
@@ -405,13 +419,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   __syncthreads();
 
   // ================================================================ stage D: g (TMEM columns 0..255, 64 per head)
+  {
+    float v[16];
+    load_global(v, st.dgbar, 1024, 0);
 #pragma unroll 1
-  for (int h = 0; h < 4; ++h)
-#pragma unroll 1
-    for (int kb = 0; kb < 4; ++kb) {
-      fill_from_global(st.dgbar + (size_t)h * 256, 1024, kb * 64);
-      run_item(12 + h * 4 + kb, (uint32_t)h * 64u, idesc64, kb == 0);
+    for (int e = 0; e < 16; ++e) {
+      const int h = e >> 2, kb = e & 3;
+      store_tile(v);
+      issue_item(12 + e, (uint32_t)h * 64u, idesc64, kb == 0);
+      if (e + 1 < 16) load_global(v, st.dgbar + (size_t)((e + 1) >> 2) * 256, 1024, ((e + 1) & 3) * 64);
+      wait_item(12 + e);
     }
+  }
   // ================================================================ stage E: lp (TMEM columns 256..511) -> st.dlp
 #pragma unroll 1
   for (int kb = 0; kb < 4; ++kb) {
@@ -476,17 +495,17 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     __syncwarp();
     const T* rows = ne16 + (size_t)b * N * 256 + lane * 8;
 #pragma unroll 1
-    for (int i0 = 0; i0 < cnt; i0 += DT_BATCH) {
-      uint4 raw[DT_BATCH];
-      int ee[DT_BATCH];
+    for (int i0 = 0; i0 < cnt; i0 += DT_BATCH3) {
+      uint4 raw[DT_BATCH3];
+      int ee[DT_BATCH3];
 #pragma unroll
-      for (int j = 0; j < DT_BATCH; ++j) {
+      for (int j = 0; j < DT_BATCH3; ++j) {
         const int i = min(i0 + j, cnt - 1);
         ee[j] = s_list[i];
         raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[ee[j]] * 256);
       }
 #pragma unroll
-      for (int j = 0; j < DT_BATCH; ++j) {
+      for (int j = 0; j < DT_BATCH3; ++j) {
         float2 acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].x)), lv[0], make_float2(0.0f, 0.0f));
         acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].y)), lv[1], acc);
         acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].z)), lv[2], acc);
