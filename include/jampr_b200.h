@@ -179,6 +179,14 @@ JAMPR_API int jampr_weight_offsets(int64_t* out, int32_t max_entries);
  * Replaces env.py:369-409 and the per-instance Python loop env.py:782-794 (+ graph_utils.py:104-141). */
 JAMPR_API int jampr_setup_instances(const jampr_dims_t* d, const jampr_instances_t* inst, void* stream);
 
+/* Start nodes of the POMO pseudo-steps (env.py:1221-1270): candidates = depot neighbourhood without the depot, reduced to
+ * the n_cand = floor((k - 1) * pomo_nbh_frac) earliest window starts; per rollout n_start distinct uniform picks
+ * (counter-based generator keyed by seed; the reference uses torch.multinomial, env.py:1258-1262), or — single_start —
+ * the sample-th earliest candidate for slot 0 only (env.py:1229-1242).  start_nodes (bs, n_start) int32 (n_start = 1
+ * with single_start), to be handed to jampr_env_reset.  Needs jampr_setup_instances (order, fixed windows). */
+JAMPR_API int jampr_pomo_start_nodes(const jampr_dims_t* d, const jampr_instances_t* inst, int32_t n_cand, int32_t n_start,
+                           int32_t single_start, uint64_t seed, int32_t* start_nodes, void* stream);
+
 /* NodeEncoder.forward, once per instance (node_encoder.py:128-155), plus the hoisted
  * node_emb_input_proj (tour_encoder.py:170-172). */
 JAMPR_API int jampr_node_encoder(const jampr_dims_t* d, const jampr_instances_t* inst,

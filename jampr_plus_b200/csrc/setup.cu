@@ -98,3 +98,57 @@ extern "C" int jampr_setup_instances(const jampr_dims_t* d, const jampr_instance
   setup_instances_kernel<<<d->n_inst, 256, smem, s>>>(*d, *inst);
   return launch_status();
 }
+
+// ---- POMO start nodes (env.py:1221-1270): per instance the depot neighbourhood without the depot (the k - 1 nodes that
+// follow the depot in `order`), reduced to the n_cand earliest window starts (stable); per rollout either the sample-th
+// of them (pomo_single_start_node) or n_start distinct ones, uniformly: a partial Fisher-Yates shuffle with draws
+// jampr_uniform(seed, rollout, 0x70000000 + t).  The reference draws with torch.multinomial on the global generator
+// (env.py:924-930, 1258-1262): same distribution, a stream that cannot be matched across devices; oracle/rng.py replays
+// this one on the CPU.
+#define POMO_MAX_CAND 256
+__global__ void pomo_start_kernel(jampr_dims_t d, jampr_instances_t p, int n_cand, int n_start, int single, uint64_t seed,
+                                  int32_t* __restrict__ out) {
+  __shared__ int16_t s_c[POMO_MAX_CAND];
+  const int i = blockIdx.x, N = d.n_nodes, k = d.k_nbh, P = d.n_samples;
+  if (threadIdx.x == 0) {
+    // insertion sort of the k - 1 candidates by window start, stable in `order` position
+    int m = 0;
+    for (int j = 1; j < k; ++j) {
+      const int16_t n = p.order[(size_t)i * N + j];
+      const float key = p.tw[((size_t)i * N + n) * 2];
+      int q = m++;
+      while (q > 0 && p.tw[((size_t)i * N + s_c[q - 1]) * 2] > key) { s_c[q] = s_c[q - 1]; --q; }
+      s_c[q] = n;
+    }
+  }
+  __syncthreads();
+  for (int smp = threadIdx.x; smp < P; smp += blockDim.x) {
+    const int b = i * P + smp;
+    if (single) {
+      out[b] = s_c[smp];
+      continue;
+    }
+    uint8_t idx[POMO_MAX_CAND];
+    for (int j = 0; j < n_cand; ++j) idx[j] = (uint8_t)j;
+    for (int t = 0; t < n_start; ++t) {
+      const float u = jampr_uniform(seed, (uint32_t)b, 0x70000000u + (uint32_t)t);
+      const int j = t + min((int)(u * (float)(n_cand - t)), n_cand - t - 1);
+      const uint8_t tmp = idx[t];
+      idx[t] = idx[j];
+      idx[j] = tmp;
+      out[(size_t)b * n_start + t] = s_c[idx[t]];
+    }
+  }
+}
+
+extern "C" int jampr_pomo_start_nodes(const jampr_dims_t* d, const jampr_instances_t* inst, int32_t n_cand, int32_t n_start,
+                                      int32_t single_start, uint64_t seed, int32_t* start_nodes, void* stream) {
+  if (!d || !inst || !start_nodes || d->n_inst <= 0 || d->k_nbh < 2 || d->k_nbh - 1 > POMO_MAX_CAND) return JAMPR_E_BADARG;
+  if (single_start) {
+    if (d->n_samples > d->k_nbh - 1) return JAMPR_E_BADARG;
+  } else if (n_cand < n_start || n_cand > d->k_nbh - 1 || n_start <= 0 || n_start > d->n_slots) {
+    return JAMPR_E_BADARG;
+  }
+  pomo_start_kernel<<<d->n_inst, 128, 0, (cudaStream_t)stream>>>(*d, *inst, n_cand, n_start, single_start, seed, start_nodes);
+  return launch_status();
+}

@@ -220,6 +220,7 @@ class RPEnv:
             self.check_feasibility = True
         self._lib = _cabi.load_library()
         self._gen = torch.Generator(device=self.device)
+        self._seed_value, self._n_resets = 0, 0
         self.clear_cache()
 
     # ------------------------------------------------------------------ plumbing
@@ -228,6 +229,7 @@ class RPEnv:
         device generator owned by the env, seeded the same way."""
         torch.manual_seed(seed)
         self._gen.manual_seed(seed)
+        self._seed_value, self._n_resets = int(seed), 0
         return [seed]
 
     def check_guards(self) -> int:
@@ -378,26 +380,28 @@ class RPEnv:
 
     # ------------------------------------------------------------------ reset (env.py:146-201, 1221-1297)
     def _pomo_start_nodes(self) -> torch.Tensor:
-        """Start nodes of the POMO pseudo-steps (env.py:1221-1270): the depot neighbourhood without the
-        depot, reduced to the earliest window starts, K distinct uniform picks per rollout; or the
-        deterministic single start node per sample."""
-        I, P, K, k = self.n_inst, self._num_samples, self.max_concurrent_vehicles, self.k_nbh_size
-        nb = self.ordered_idx[:, 1:k].long()
-        tws = self.tw[:, :, 0].gather(1, nb)
-        srt = torch.sort(tws, dim=-1, stable=True).indices
+        """Start nodes of the POMO pseudo-steps (env.py:1221-1270) on the device (jampr_pomo_start_nodes): the depot
+        neighbourhood without the depot, reduced to the earliest window starts, K distinct uniform picks per rollout
+        — or the deterministic single start node per sample.  Every reset() since the last seed() uses a fresh stream."""
+        P, K, k = self._num_samples, self.max_concurrent_vehicles, self.k_nbh_size
         if self.pomo_single_start_node:
             if P > k - 1:
                 raise RuntimeError(f"sample set for POMO has size {k - 1} which is too small for {P} samples!")
-            return nb.gather(1, srt[:, :P]).reshape(-1, 1).to(torch.int32).contiguous()
-        kk = math.floor((k - 1) * self.pomo_nbh_frac)
-        if kk < K:
-            raise RuntimeError(f"sample set for POMO has size {kk} which is too small for {P} samples! "
-                               f"Try increasing 'k_nbh_frac' of env.")
-        cand = nb.gather(1, srt[:, :kk])
-        pick = torch.multinomial(torch.ones(self.bs, kk, device=self.device), K, replacement=False,
-                                 generator=self._gen)
-        cand = cand.repeat_interleave(P, dim=0)
-        return cand.gather(1, pick).to(torch.int32).contiguous()
+            kk, n_start = k - 1, 1
+        else:
+            kk, n_start = math.floor((k - 1) * self.pomo_nbh_frac), K
+            if kk < K:
+                raise RuntimeError(f"sample set for POMO has size {kk} which is too small for {P} samples! "
+                                   f"Try increasing 'k_nbh_frac' of env.")
+        if k - 1 > 256:
+            raise NotImplementedError("POMO start selection supports neighbourhoods of up to 257 nodes")
+        out = torch.empty(self.bs, n_start, dtype=torch.int32, device=self.device)
+        seed = (int(self._seed_value) * 0x9E3779B1 + self._n_resets * 0x85EBCA77 + 0x5bd1e995) & 0xFFFFFFFFFFFFFFFF
+        self._n_resets += 1
+        _cabi.check(self._lib.jampr_pomo_start_nodes(self._dims, self._inst, kk, n_start,
+                                                     int(self.pomo_single_start_node), seed, _cabi.ptr(out),
+                                                     self._stream()), "jampr_pomo_start_nodes")
+        return out
 
     def reset(self, start_nodes: Optional[torch.Tensor] = None) -> RPObs:
         """Reset the simulator and return the initial observation.  ``start_nodes`` (bs, n_start) overrides

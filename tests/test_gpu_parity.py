@@ -516,3 +516,52 @@ def test_static_node_embedding_against_reference():
         pol(obs)
         err = float((env._static_emb[0].cpu() - torch.from_numpy(g["static_node_emb0"])).abs().max())
         assert err <= tol, (prec, err)
+
+
+def test_pomo_start_nodes_kernel_against_cpu_twin():
+    """Start nodes of the POMO pseudo-steps (env.py:1221-1270) drawn on the device: candidate set = the earliest-window
+    fraction of the depot neighbourhood (compared with a numpy restatement), K distinct picks per rollout reproduced on
+    the CPU from the generator's twin (oracle/rng.py); the single-start variant equals the reference trace's nodes."""
+    import math
+    from oracle.rng import uniform_scalar
+    from jampr_plus_b200 import RPEnv
+    from jampr_plus_b200.synth import sample_instances
+    inst = sample_instances(5, graph_size=60, seed=21)
+    env = RPEnv(max_concurrent_vehicles=3, k_nbh_frac=0.3, pomo=True, pomo_nbh_frac=0.5, num_samples=7, inference=True,
+                device="cuda")
+    env.seed(99)
+    env.load_data(inst)
+    env.reset()
+    got = env._start_nodes.cpu().numpy()
+    k, K, P = env.k_nbh_size, 3, 7
+    kk = math.floor((k - 1) * 0.5)
+    order = env.ordered_idx.cpu().numpy()
+    tws = env.tw[:, :, 0].cpu().numpy()
+    seed = (99 * 0x9E3779B1 + 0 * 0x85EBCA77 + 0x5bd1e995) & 0xFFFFFFFFFFFFFFFF
+    for i in range(len(inst)):
+        nb = order[i, 1:k]
+        cand = nb[np.argsort(tws[i, nb], kind="stable")][:kk]
+        for s in range(P):
+            b = i * P + s
+            idx = list(range(kk))
+            exp = []
+            for t in range(K):
+                u = np.float32(uniform_scalar(seed, b, 0x70000000 + t))
+                j = t + min(int(np.float32(u * np.float32(kk - t))), kk - t - 1)
+                idx[t], idx[j] = idx[j], idx[t]
+                exp.append(int(cand[idx[t]]))
+            assert got[b].tolist() == exp, (i, s)
+            assert len(set(exp)) == K
+    # a second reset draws from a fresh stream; re-seeding reproduces the first one
+    env.load_data(inst)
+    env.reset()
+    assert not np.array_equal(env._start_nodes.cpu().numpy(), got)
+    env.seed(99)
+    env.load_data(inst)
+    env.reset()
+    assert np.array_equal(env._start_nodes.cpu().numpy(), got)
+    # deterministic single start node: the reference's own nodes (recorded trace)
+    g = load_case("g51_upd2")
+    env2, _ = _make(g)
+    env2.reset()
+    assert np.array_equal(env2._start_nodes.cpu().numpy().reshape(-1), _sn(g).numpy().reshape(-1))
