@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      if (i + 1 < DT_ITEMS) issue_b(i + 1);          // its buffer was last read by item i - 1, complete (waited)
       mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       const uint32_t bh = b_addr + (uint32_t)(i & 1) * 65536u, bl = bh + 32768u;
@@ -222,6 +221,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
         umma_f16(tmem + d_col, dah, dbl, idesc, 1u);
       }
       umma_commit(bar_mma);
+      if (i + 1 < DT_ITEMS) issue_b(i + 1);          // off the critical path; its buffer was last read by item i - 1 (complete)
     }
   };
   auto wait_item = [&](int i) {
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
         ok = st.mask[(size_t)b * A + e] == 0;
       }
       const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (ok) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (int16_t)e;
+      if (ok) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (int16_t)(e | ((e / k) << 10));      // action | slot << 10
       cnt += __popc(m);
     }
     // per-head glimpse query: lane owns columns 8 lane .. 8 lane + 7
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       for (int j = 0; j < DT_BATCH; ++j) {
         const int i = min(i0 + j, cnt - 1);
         ee[j] = s_list[i];
-        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[ee[j]] * 256);
+        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[ee[j] & 1023] * 256);
       }
 #pragma unroll
       for (int j = 0; j < DT_BATCH; ++j) {
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
         const float z = warp_sum4(dd[0], dd[1], dd[2], dd[3], lane);
         if ((lane & 7) == 0 && i0 + j < cnt) {
           const int h = ((lane >> 4) << 1) | ((lane >> 3) & 1);
-          s_p[(i0 + j) * 4 + h] = (z + s_qt[h * 4 + ee[j] / k]) * 0.125f;
+          s_p[(i0 + j) * 4 + h] = (z + s_qt[h * 4 + (ee[j] >> 10)]) * 0.125f;
         }
       }
     }
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     for (int t = 0; t < K; ++t) {
       float ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       for (int i = lane; i < cnt; i += 32) {
-        if (s_list[i] / k == t) {
+        if ((s_list[i] >> 10) == t) {
           const float4 pw = lds_f32x4(p_saddr + (uint32_t)i * 16u);
           ps[0] += pw.x; ps[1] += pw.y; ps[2] += pw.z; ps[3] += pw.w;
         }
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
 #pragma unroll
       for (int j = 0; j < DT_BATCH; ++j) {
         const int i = min(i0 + j, cnt - 1);
-        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[s_list[i]] * 256);
+        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[s_list[i] & 1023] * 256);
       }
 #pragma unroll
       for (int j = 0; j < DT_BATCH; ++j) {
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
         s_logit[e] = -INFINITY;
       }
       const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (ok) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (int16_t)e;
+      if (ok) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (int16_t)(e | ((e / k) << 10));
       cnt += __popc(m);
     }
     float2 lv[4];
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       for (int j = 0; j < DT_BATCH3; ++j) {
         const int i = min(i0 + j, cnt - 1);
         ee[j] = s_list[i];
-        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[ee[j]] * 256);
+        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[ee[j] & 1023] * 256);
       }
 #pragma unroll
       for (int j = 0; j < DT_BATCH3; ++j) {
@@ -511,10 +511,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
         acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].z)), lv[2], acc);
         acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].w)), lv[3], acc);
         const float z = warp_sum(acc.x + acc.y);
-        const int t = ee[j] / k;
-        const float ltv = (t == 0) ? lt[0] : (t == 1) ? lt[1] : (t == 2) ? lt[2] : lt[3];
-        if (lane == 0 && i0 + j < cnt) s_logit[ee[j]] = 10.0f * tanhf((z + ltv) * 0.0625f);
+        if (lane == 0 && i0 + j < cnt) s_logit[ee[j] & 1023] = z;          // raw dot product; the clip follows, vectorised
       }
+    }
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) {
+      const int v = s_list[i], e = v & 1023, t = v >> 10;
+      const float ltv = (t == 0) ? lt[0] : (t == 1) ? lt[1] : (t == 2) ? lt[2] : lt[3];
+      s_logit[e] = 10.0f * tanhf((s_logit[e] + ltv) * 0.0625f);
     }
     __syncwarp();
     // ---- masked log-softmax + selection, same rules as decoder.cu / policy_tc2.cu
@@ -600,7 +604,7 @@ static int launch_dt(const DtArgs& a, size_t smem, cudaStream_t s) {
 // Returns JAMPR_E_TOOLARGE when the configuration does not fit (caller keeps the fused decoder).
 int jampr_decoder_tc(const jampr_dims_t* d, const jampr_weights_t* w, const jampr_state_t* st, int step_no,
                      int decode_type, uint64_t seed, const float* uniforms, cudaStream_t s) {
-  if (d->n_slots > 4) return JAMPR_E_TOOLARGE;
+  if (d->n_slots > 4 || d->n_slots * d->k_nbh > 1023) return JAMPR_E_TOOLARGE;
   if (!st->ne16 || !st->dq || !st->dte || !st->dqp || !st->dgbar || !st->dlp) return JAMPR_E_BADARG;
   if (!w->blob_bf16 || w->n_bf16 < (int64_t)W16_END) return JAMPR_E_BADARG;
   const size_t smem = dt_smem_bytes(d);
@@ -618,5 +622,5 @@ int jampr_decoder_tc(const jampr_dims_t* d, const jampr_weights_t* w, const jamp
 }
 
 int jampr_decoder_tc_fits(const jampr_dims_t* d) {
-  return d->n_slots <= 4 && dt_smem_bytes(d) <= 227 * 1024;
+  return d->n_slots <= 4 && d->n_slots * d->k_nbh <= 1023 && dt_smem_bytes(d) <= 227 * 1024;      // action index: 10 bits
 }
