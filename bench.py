@@ -450,10 +450,18 @@ def main():
         cap = env.graph_size + env.max_vehicle_number + 1
         step = env._step
         fused = args.precision != "fp32"      # tensor-core path: GNN + decoder are ONE kernel per step
+        split = fused and bs >= _cabi.SPLIT_MIN_ROLLOUTS and pol.tc_variant in (0, 3)
+        dec_evs = []
         while step <= cap:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            if fused:
+            if split:          # the two launches of the policy step one by one: GNN kernel, then the 128-rollout decoder
+                m = torch.cuda.Event(enable_timing=True)
+                _cabi.check(lib.jampr_policy_step_part(d, p, w, st.struct(), 1, step, 0, 0, None, 1, S), "jampr_policy_step_part")
+                m.record()
+                _cabi.check(lib.jampr_policy_step_part(d, p, w, st.struct(), 1, step, 0, 0, None, 2, S), "jampr_policy_step_part")
+                dec_evs.append(m)
+            elif fused:
                 _cabi.check(lib.jampr_policy_step(d, p, w, st.struct(), 1, step, 0, 0, None, S), "jampr_policy_step")
             else:
                 _cabi.check(lib.jampr_tour_encoder(d, p, w, st.struct(), step, S), "jampr_tour_encoder")
@@ -503,6 +511,23 @@ def main():
                 "share_of_step": avg_ms * len(live) / (ms_res / args.steps)}
         if env_roof is not None:
             roof["secondary"] = env_roof
+        if dec_evs:
+            # the decoder launch against the HBM roofline.  Algorithmic bytes per rollout and step (A*D*s
+            # for the candidate rows once, "fused behind set_proj") + the hand-over vectors between its stages
+            # (q 2 KB, tour embeddings 3 KB, qp / gbar 4 KB each written + read, lp 1 KB written + read)
+            live_dec = [m.elapsed_time(b) for i, (m, (_, b)) in enumerate(zip(dec_evs, evs)) if env._step + i <= done2]
+            live_gnn = [a.elapsed_time(m) for i, (m, (a, _)) in enumerate(zip(dec_evs, evs)) if env._step + i <= done2]
+            dec_ms = float(np.mean(live_dec))
+            dec_bytes = (A_act * 256 * 2 + 2048 + 3072 + 2 * 4096 + 2 * 4096 + 2 * 1024) * bs
+            hbm = float(peaks.get("hbm_gbs", 6650.0))
+            dtr = tr.get("per_kernel", {}).get("decoder_tc_kernel") if traffic is not None else None
+            roof["decoder"] = {"bound": "hbm", "kernel": "decoder_tc_kernel (second launch of the policy step)",
+                               "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                               "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / hbm,
+                               "traffic": None if not dtr else dtr["dram__bytes_read.sum"] + dtr["dram__bytes_write.sum"],
+                               "bytes_per_launch": dec_bytes, "avg_ms": dec_ms,
+                               "share_of_step": dec_ms * len(live_dec) / (ms_res / args.steps)}
+            roof["gnn_kernel_avg_ms"] = float(np.mean(live_gnn))
         par = parity_probe(dev, args.precision)
 
     # ---- BASELINE config 4 (GH-1000 shape, weak scaling) and configs 1 / 5 (LNS; sharded sub-problems for N > 1): all ranks
@@ -562,10 +587,13 @@ def main():
         return
     n_it = done_step - ENV_KW["max_concurrent_vehicles"] + 1          # live iterations of the device loop
     enq = env.graph_size + env.max_vehicle_number + 1 - ENV_KW["max_concurrent_vehicles"] + 1
-    # own kernels per pass: setup_instances 1, edge-table prepare 1, node encoder (input, 3 GraphConv launches, projection,
-    # h0: 6 on the tensor-core path, 1 in fp32), env_reset 1, per enqueued step policy 1 (fp32: 2) + env 2, gather_best 1
+    # own kernels per pass: setup_instances 1, POMO start nodes 1, edge-table prepare 1, node encoder (input, 3 GraphConv
+    # launches, projection, h0: 6 on the tensor-core path, 1 in fp32), env_reset 1, per enqueued step policy (GNN kernel +
+    # 128-rollout decoder: 2; fused variant 1; fp32: tour encoder + decoder 2) + env 2, gather_best 1
     tc = args.precision != "fp32"
-    launches = args.steps * ((10 if tc else 4) + (3 if tc else 4) * enq)
+    split_run = tc and bs >= _cabi.SPLIT_MIN_ROLLOUTS and pol.tc_variant in (0, 3)
+    per_step = (4 if split_run else 3) if tc else 4
+    launches = args.steps * ((11 if tc else 5) + per_step * enq)
     in_bytes = sum(v.numel() * 4 for v in pinned.values())
     out_bytes = out_cost.numel() * 4 + out_plan.numel() * 2
     total_rollouts = bs * world

@@ -266,6 +266,13 @@ JAMPR_API int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t* 
                       const jampr_state_t* st, int32_t graph_fresh, int32_t step_no,
                       int32_t decode_type, uint64_t seed, const float* uniforms, void* stream);
 
+/* The two launches of jampr_policy_step's split variant separately (part 1 = per-rollout GNN kernel, part 2 = decoder over
+ * 128 rollouts per CTA; csrc/policy_tc2.cu, csrc/decoder_tc.cu), for callers that time them one by one (bench.py).
+ * JAMPR_E_UNSUPPORTED when the configuration is not served by that variant.  Replaces nothing in the reference. */
+JAMPR_API int jampr_policy_step_part(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                           const jampr_state_t* st, int32_t graph_fresh, int32_t step_no, int32_t decode_type,
+                           uint64_t seed, const float* uniforms, int32_t part, void* stream);
+
 /* The per-step tour-graph GNN alone (tour_encoder.py:159-198 + the node_emb projection :217-218): what
  * jampr_policy_step runs when graph_fresh = 1.  Exposed so that callers (tests, bench.py) can check and
  * time the dominant kernel in isolation. */

@@ -58,7 +58,7 @@ RM_COMPLETE_MODES = {"random": 0, "smallest": 1}
 SYMBOLS = ("jampr_abi_version", "jampr_weight_blob_floats", "jampr_weight_blob16_elems", "jampr_weight_offsets", "jampr_setup_instances",
            "jampr_node_encoder", "jampr_env_reset", "jampr_env_step", "jampr_env_resume", "jampr_env_import_finish",
            "jampr_tour_encoder", "jampr_policy_step", "jampr_rollout", "jampr_gather_best", "jampr_true_cost",
-           "jampr_selftest_umma", "jampr_env_import_tours", "jampr_lns_destroy", "jampr_local_search", "jampr_pomo_start_nodes")
+           "jampr_selftest_umma", "jampr_env_import_tours", "jampr_lns_destroy", "jampr_local_search", "jampr_pomo_start_nodes", "jampr_policy_step_part")
 
 _lib = None
 
@@ -84,6 +84,7 @@ def load_library():
     lib.jampr_env_resume.argtypes = [PD, PI, PS, C.c_int32, _p]
     lib.jampr_tour_encoder.argtypes = [PD, PI, PW, PS, C.c_int32, _p]
     lib.jampr_policy_step.argtypes = [PD, PI, PW, PS, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _p, _p]
+    lib.jampr_policy_step_part.argtypes = [PD, PI, PW, PS, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _p, C.c_int32, _p]
     lib.jampr_rollout.argtypes = [PD, PI, PW, PS, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, _p]
     lib.jampr_gather_best.argtypes = [PD, PS, _p, _p, _p, _p]
     lib.jampr_true_cost.argtypes = [PD, PI, PS, _p, _p]

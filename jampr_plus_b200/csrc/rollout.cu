@@ -132,6 +132,23 @@ extern "C" int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t*
   return jampr_decoder_launch(d, inst, st, w->blob, step_no, decode_type, seed, uniforms, s);
 }
 
+// The two launches of the split policy step one by one (part 1 = per-rollout GNN kernel in split mode, part 2 = the
+// 128-rollout decoder), so that callers can time them separately (bench.py roofline entries).  Only for configurations the
+// split variant serves; jampr_policy_step is the product entry point.
+extern "C" int jampr_policy_step_part(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
+                                      const jampr_state_t* st, int32_t graph_fresh, int32_t step_no, int32_t decode_type,
+                                      uint64_t seed, const float* uniforms, int32_t part, void* stream) {
+  const int rc = check_policy_args(d, inst, w);
+  if (rc) return rc;
+  if (!st || w->precision == JAMPR_PREC_F32 || d->n_nodes > JAMPR_TILE_NODES || (part != 1 && part != 2)) return JAMPR_E_BADARG;
+  if (!(st->ne16 && st->dq && st->dte && st->dqp && st->dgbar && st->dlp) || !jampr_decoder_tc_fits(d)) return JAMPR_E_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (part == 1)
+    return jampr_policy_step_tc2(d, inst, w, st, graph_fresh, step_no, decode_type, seed, uniforms,
+                                 (d->upd_step != 1) || st->logp != nullptr, 1, s);
+  return jampr_decoder_tc(d, w, st, step_no, decode_type, seed, uniforms, s);
+}
+
 extern "C" int jampr_rollout(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,
                              const jampr_state_t* st, int32_t first_step, int32_t first_fresh, int32_t decode_type,
                              uint64_t seed, int32_t max_steps, void* stream) {
