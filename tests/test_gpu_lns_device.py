@@ -154,3 +154,58 @@ def test_all_device_lns_loop():
             load += inst.demands[n]
             prev = n
         assert load <= 1.0 + 1e-6, "capacity violated"
+
+
+def test_edge_cases_of_the_device_solution_io():
+    """Empty and degenerate inputs: a solution without tours (everything unvisited), a solution whose every tour is a
+    singleton, a partial tour that fills the tour buffer, too many tours (the reference's RuntimeError), destruction
+    of solutions with fewer candidate tours than num_partial, local search on an empty / single-tour plan."""
+    from jampr_plus_b200 import RPEnv
+    from jampr_plus_b200.synth import sample_instances
+    inst = sample_instances(1, graph_size=40, seed=8)
+    env = RPEnv(inference=True, device="cuda", max_concurrent_vehicles=2, k_nbh_frac=0.5, pomo=False, num_samples=4)
+    env.load_data(inst)
+    env.reset()
+    K_max, L = env.state.K_max, env.state.L
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # no tours at all / only singletons -> the state of a fresh reset (two fresh vehicles, nothing visited)
+        for sol in ([[[], [[3]], [[5], [7]], []]],):
+            for path in ("device", "host"):
+                e = RPEnv(inference=True, device="cuda", max_concurrent_vehicles=2, k_nbh_frac=0.5, pomo=False, num_samples=4)
+                e.load_data(inst)
+                e.reset()
+                (e.import_sol if path == "device" else e._import_sol_host)(sol)
+                assert int(e.state["visited"].sum()) == 0 and e._step == 0
+                assert e.state["row"].tolist() == [[0, 1]] * 4 and float(e.state["total"].abs().sum()) == 0.0
+        # more tours than vehicles: the reference's RuntimeError (env.py:660-662)
+        too_many = [[[[0, 1 + t, 0] for t in range(K_max + 1)]] * 4]
+        with pytest.raises(RuntimeError):
+            env.load_data(inst)
+            env.reset()
+            env.import_sol(too_many)
+        # destruction with a single candidate tour and num_partial = 2, complete-route removal on an empty rest
+        env.load_data(inst)
+        env.reset()
+        plan = torch.zeros(4, K_max, L, dtype=torch.int16, device="cuda")
+        plan[:, 0, :5] = torch.tensor([4, 9, 2, 7, 11], dtype=torch.int16)
+        plan[:, 1, 0] = 13                                   # a singleton tour: always dropped
+        env.state["plan"].copy_(plan)
+        env.state["total"].copy_(torch.tensor([1.0, 2.0, 3.0, 4.0], device="cuda"))
+        env.destruct(num_best=1, num_other=1, num_partial=2, rm_partial_mode="random_cut", frac_rm_complete_routes=0.5,
+                     seed=3, iteration=1)
+        tours, kind = (t.cpu().numpy() for t in env._destroy_buf)
+        for b in range(4):
+            assert kind[b].tolist()[:1] == [2] and not kind[b][1:].any()
+            t = tours[b, 0][tours[b, 0] > 0].tolist()
+            assert 1 <= len(t) <= 3 and t == [4, 9, 2, 7, 11][: len(t)]
+        # local search: empty plan and single tour are fixed points or improve, never break
+        env.state["plan"].zero_()
+        cost, moves = env.local_search(10, update_totals=False)
+        assert float(cost.abs().sum()) == 0.0 and int(moves.sum()) == 0
+        env.state["plan"][:, 0, :3] = torch.tensor([4, 9, 2], dtype=torch.int16, device="cuda")
+        cost, moves = env.local_search(10, update_totals=False)
+        after = env.state["plan"][:, :, :].cpu().numpy()
+        for b in range(4):
+            assert sorted(after[b][after[b] > 0].tolist()) == [2, 4, 9]
+        assert torch.isfinite(cost).all()

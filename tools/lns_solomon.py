@@ -128,6 +128,15 @@ def bench_lns(dev="cuda", precision="fp16", time_limit=20.0, cpu_time_limit=10.0
            "ms_per_iteration": 1e3 * dt / max(lns.step, 1), "sub_problems_per_iteration": ENV_KW["num_samples"] * world,
            "incumbent_env_cost": cost, "incumbent_tour_cost": true_cost, "n_gpus": world,
            "n_tours": int((plan[:, 0] > 0).sum())}
+    if world == 1:
+        # the same loop with the device local search (relocate / 2-opt*) on every repaired solution, half the budget
+        lns_ls = LNS(inst, pol, env, seed=1234, selection_mode="random", ls_step=1)
+        t0 = time.time()
+        _, c_ls, tc_ls = lns_ls.search_device(time_limit=0.5 * time_limit)
+        dt_ls = time.time() - t0
+        out["with_local_search"] = {"time_limit_s": 0.5 * time_limit, "seconds": dt_ls, "iterations": lns_ls.step,
+                                    "ms_per_iteration": 1e3 * dt_ls / max(lns_ls.step, 1), "incumbent_env_cost": c_ls,
+                                    "incumbent_tour_cost": tc_ls, "ls": "jampr_local_search, ls_step = 1, <= 200 moves per solution"}
     if world == 1 and cpu_time_limit > 0:
         class A:
             pass
