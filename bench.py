@@ -622,7 +622,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_cpu = args.cpu_sample if args.cpu_sample > 0 else 2
+        n_cpu = args.cpu_sample if args.cpu_sample > 0 else 6      # ~10-20 s of the reference on the host cores
         kind, r, t, desc = cpu_arm(raw, 0, n_cpu, threads)
         if kind == "port" and args.cpu_sample <= 0:      # the port is ~5x faster than the reference: a larger sample
             kind, r, t, desc = cpu_arm(raw, 0, 12, threads)
