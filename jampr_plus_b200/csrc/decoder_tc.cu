@@ -1,7 +1,9 @@
 // Split decoder of the tensor-core policy step (sm_100a): attn_decoder.py:62-98 + policy.py:203-227 for 128 rollouts
-// per CTA.  policy_tc2.cu (split mode) leaves per rollout the 16-bit node-embedding rows (st.ne16), the query
-// (st.dq, policy.py:179-182) and the tour embeddings (st.dte) in HBM; this kernel runs
+// per CTA.  policy_tc2.cu (split mode) leaves per rollout the 16-bit node-embedding rows (st.ne16), their column mean /
+// max (st.dq), the per-tour means of h and the tour features (st.dqp) in HBM; this kernel runs
 //
+//   stage T   tour_emb[t] (per-tour-mean half) = mean_h[t] W_to2^T      K x GEMM 128 x 256 x 128   (tour_encoder.py:202-213)
+//             + per rollout: feature half, query q = [mean + mean, max + max]                   (policy.py:179-182)
 //   stage A   ctxt = q W_c^T                       GEMM 128 x 256 x 512          (attn_decoder.py:73)
 //   stage B   qp_h = W_gk,h^T ctxt_h  (4 heads)    4 GEMMs 128 x 256 x 64        (set_proj moved to the query side)
 //   phase C   per rollout, one warp: glimpse scores qp_h . (node_emb[n_a] + tour_emb[t_a]) over the FEASIBLE actions,
@@ -27,11 +29,12 @@
 #define DT_M 128
 #define DT_BATCH 8             // node-embedding rows in flight per lane in the per-rollout passes
 #define DT_BATCH3 16           // same in the logit pass, which keeps few other registers live
-#define DT_ITEMS 32            // B tiles consumed: 8 (stage A) + 4 (B) + 16 (D) + 4 (E)
+#define DT_ITEMS 32            // B tiles consumed after stage T (2 per vehicle slot): 8 (stage A) + 4 (B) + 16 (D) + 4 (E)
 
 struct DtArgs {
   jampr_dims_t d;
   jampr_state_t st;
+  const float* w;        // fp32 blob: folded tour-feature branch (OFF_TOF_*)
   const void* w16;
   const float* uniforms;
   uint64_t seed;
@@ -69,7 +72,9 @@ __device__ __forceinline__ void write_a16(uint8_t* sAhi, uint8_t* sAlo, int r, i
 }
 
 // B tile of item i inside one part of the decoder blob: element offset and element count
-__device__ __forceinline__ void dt_item_src(int i, uint32_t& off, uint32_t& elems) {
+__device__ __forceinline__ void dt_item_src(int i, int n_t, uint32_t& off, uint32_t& elems) {
+  if (i < n_t) { off = WD_TO + (uint32_t)(i & 1) * WD_TILE; elems = WD_TILE; return; }      // stage T: (slot, K-block) items
+  i -= n_t;
   if (i < 8) { off = WD_C + (uint32_t)i * WD_TILE; elems = WD_TILE; }
   else if (i < 12) { off = WD_GK + (uint32_t)(i - 8) * WD_TILE; elems = WD_TILE; }
   else if (i < 28) { off = WD_GV + (uint32_t)(i - 12) * (WD_TILE / 4); elems = WD_TILE / 4; }
@@ -130,10 +135,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     return;
   }
 
+  const int n_t = 2 * K, n_items = n_t + DT_ITEMS;      // stage T: two K-block items per vehicle slot
   const uint8_t* wdec = reinterpret_cast<const uint8_t*>(a.w16) + (size_t)W16_DEC * 2;
   auto issue_b = [&](int i) {          // one thread
     uint32_t off, elems;
-    dt_item_src(i, off, elems);
+    dt_item_src(i, n_t, off, elems);
     const int buf = i & 1;
     mbar_arrive_expect_tx(&full[buf], elems * 4u);
     bulk_g2s(sB + buf * 65536, wdec + (size_t)off * 2, elems * 2u, &full[buf]);
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
         umma_f16(tmem + d_col, dah, dbl, idesc, 1u);
       }
       umma_commit(bar_mma);
-      if (i + 1 < DT_ITEMS) issue_b(i + 1);          // off the critical path; its buffer was last read by item i - 1 (complete)
+      if (i + 1 < n_items) issue_b(i + 1);           // off the critical path; its buffer was last read by item i - 1 (complete)
     }
   };
   auto wait_item = [&](int i) {
@@ -233,6 +239,87 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     wait_item(i);
   };
 
+  // ================================================================ stage T: per-tour-mean half of the tour embeddings
+  // tour_encoder.py:202-213: tour_emb[t] = W_to [input_proj(features_t) | mean_h[t]] + b.  The mean half is a GEMM over
+  // the 128 rollouts of the tile per vehicle slot (A = the per-tour means the GNN kernel left in st.dqp[:, t, 0..127]);
+  // its raw result goes to st.dte, the feature half (folded 5 x 256 matrix) is added in the pass below.
+  {
+    float v[16];
+    load_global(v, st.dqp, 1024, 0);
+#pragma unroll 1
+    for (int e = 0; e < n_t; ++e) {
+      const int t = e >> 1, kb = e & 1;
+      store_tile(v);
+      issue_item(e, 0u, idesc256, kb == 0);
+      if (e + 1 < n_t) load_global(v, st.dqp + (size_t)((e + 1) >> 1) * 256, 1024, ((e + 1) & 1) * 64);
+      wait_item(e);
+      if (kb == 1) {
+        drain_to_global(0u, st.dte + (size_t)t * 256, 1024);
+        tc_fence_before();
+      }
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- per rollout (one warp, lane = 8 columns): tour embeddings and the decoder query (policy.py:179-182)
+  // q = [mean_n(node_emb) + mean_t(tour_emb), max_n(node_emb) + max_t(tour_emb)]; st.dq arrives holding the node statistics
+  {
+  const int c0 = lane * 8;
+  float bias[8], wt[5][8];                 // folded tour-feature branch for this lane's columns: the same for every rollout
+  {
+    const float4* pb = reinterpret_cast<const float4*>(a.w + OFF_TOF_B + c0);
+    const float4 x = __ldg(pb), y = __ldg(pb + 1);
+    bias[0] = x.x; bias[1] = x.y; bias[2] = x.z; bias[3] = x.w; bias[4] = y.x; bias[5] = y.y; bias[6] = y.z; bias[7] = y.w;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float4* pw = reinterpret_cast<const float4*>(a.w + OFF_TOF_WT + i * 256 + c0);
+      const float4 u = __ldg(pw), z = __ldg(pw + 1);
+      wt[i][0] = u.x; wt[i][1] = u.y; wt[i][2] = u.z; wt[i][3] = u.w; wt[i][4] = z.x; wt[i][5] = z.y; wt[i][6] = z.z; wt[i][7] = z.w;
+    }
+  }
+#pragma unroll 1
+  for (int rr = warp; rr < DT_M; rr += DT_WARPS) {
+    const int b = b0 + rr;
+    if (b >= bs) break;
+    if (jampr_rollout_idle(st, b, K)) continue;
+    float sum[8], mx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; mx[j] = -INFINITY; }
+    for (int t = 0; t < K; ++t) {
+      float* pt = st.dte + ((size_t)b * 4 + t) * 256 + c0;
+      const float* pf = st.dqp + ((size_t)b * 4 + t) * 256 + 128;
+      const float4 x = *reinterpret_cast<const float4*>(pt), y = *reinterpret_cast<const float4*>(pt + 4);
+      const float gm[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+      float f[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) f[i] = pf[i];
+      float te[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = bias[j];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v = fmaf(f[i], wt[i][j], v);
+        v += gm[j];
+        te[j] = v;
+        sum[j] += v;
+        mx[j] = fmaxf(mx[j], v);
+      }
+      *reinterpret_cast<float4*>(pt) = make_float4(te[0], te[1], te[2], te[3]);
+      *reinterpret_cast<float4*>(pt + 4) = make_float4(te[4], te[5], te[6], te[7]);
+    }
+    float* pq = st.dq + (size_t)b * 512 + c0;
+    const float4 m0 = *reinterpret_cast<const float4*>(pq), m1 = *reinterpret_cast<const float4*>(pq + 4);
+    const float4 x0 = *reinterpret_cast<const float4*>(pq + 256), x1 = *reinterpret_cast<const float4*>(pq + 260);
+    // same operation order as the fused kernel: nmean + sum / K, nmax + max
+    *reinterpret_cast<float4*>(pq) = make_float4(m0.x + sum[0] / (float)K, m0.y + sum[1] / (float)K, m0.z + sum[2] / (float)K, m0.w + sum[3] / (float)K);
+    *reinterpret_cast<float4*>(pq + 4) = make_float4(m1.x + sum[4] / (float)K, m1.y + sum[5] / (float)K, m1.z + sum[6] / (float)K, m1.w + sum[7] / (float)K);
+    *reinterpret_cast<float4*>(pq + 256) = make_float4(x0.x + mx[0], x0.y + mx[1], x0.z + mx[2], x0.w + mx[3]);
+    *reinterpret_cast<float4*>(pq + 260) = make_float4(x1.x + mx[4], x1.y + mx[5], x1.z + mx[6], x1.w + mx[7]);
+  }
+  }
+  __threadfence_block();
+  __syncthreads();
+
   // ================================================================ stage A: ctxt (TMEM columns 0..255)
   {
     float v[16];
@@ -240,16 +327,16 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
 #pragma unroll 1
     for (int kb = 0; kb < 8; ++kb) {
       store_tile(v);
-      issue_item(kb, 0u, idesc256, kb == 0);
+      issue_item(n_t + kb, 0u, idesc256, kb == 0);
       if (kb + 1 < 8) load_global(v, st.dq, 512, (kb + 1) * 64);
-      wait_item(kb);
+      wait_item(n_t + kb);
     }
   }
   // ================================================================ stage B: qp_h (TMEM columns 256..511) -> st.dqp
 #pragma unroll 1
   for (int h = 0; h < 4; ++h) {
     fill_from_tmem((uint32_t)h * 64u);
-    run_item(8 + h, 256u, idesc256, true);
+    run_item(n_t + 8 + h, 256u, idesc256, true);
     drain_to_global(256u, st.dqp + (size_t)h * 256, 1024);
     tc_fence_before();           // the next item's MMAs overwrite these columns after the block barrier in run_item
   }
@@ -426,16 +513,16 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     for (int e = 0; e < 16; ++e) {
       const int h = e >> 2, kb = e & 3;
       store_tile(v);
-      issue_item(12 + e, (uint32_t)h * 64u, idesc64, kb == 0);
+      issue_item(n_t + 12 + e, (uint32_t)h * 64u, idesc64, kb == 0);
       if (e + 1 < 16) load_global(v, st.dgbar + (size_t)((e + 1) >> 2) * 256, 1024, ((e + 1) & 3) * 64);
-      wait_item(12 + e);
+      wait_item(n_t + 12 + e);
     }
   }
   // ================================================================ stage E: lp (TMEM columns 256..511) -> st.dlp
 #pragma unroll 1
   for (int kb = 0; kb < 4; ++kb) {
     fill_from_tmem((uint32_t)kb * 64u);
-    run_item(28 + kb, 256u, idesc256, kb == 0);
+    run_item(n_t + 28 + kb, 256u, idesc256, kb == 0);
   }
   drain_to_global(256u, st.dlp, 256);
   tc_fence_before();
@@ -612,6 +699,7 @@ int jampr_decoder_tc(const jampr_dims_t* d, const jampr_weights_t* w, const jamp
   DtArgs a;
   a.d = *d;
   a.st = *st;
+  a.w = w->blob;
   a.w16 = w->blob_bf16;
   a.uniforms = uniforms;
   a.seed = seed;

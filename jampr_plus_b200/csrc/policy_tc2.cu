@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   uint4 pre[8];
   float4 pref[8];
   if (!SPLIT) mvf_prefetch(w + OFF_CTXT_WT, 512, pref);   // first weight batch of stage (c): no dependency, hides its latency
-  if (mv) matvec2<T, 2, 4>(w16 + W16_TO2, 128, smem_u32(s_mean), 128, s_part);     // NV = 4 >= K slots (K <= 4 here)
+  if (mv && !SPLIT) matvec2<T, 2, 4>(w16 + W16_TO2, 128, smem_u32(s_mean), 128, s_part);     // NV = 4 >= K slots (K <= 4 here)
   // (a) column mean / max of node_emb over the nodes (policy.py:179-181): thread = column pair x row parity
   {
     const int c2 = tid & 127, half = tid >> 7;
@@ -860,24 +860,27 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       st.ne_stats[(size_t)b * 512 + tid] = nmean;
       st.ne_stats[(size_t)b * 512 + 256 + tid] = nmax;
     }
-    float sm = 0.0f, mx = -INFINITY;
-    for (int t = 0; t < K; ++t) {
-      float v = __ldg(w + OFF_TOF_B + tid);
-#pragma unroll
-      for (int i = 0; i < 5; ++i) v = fmaf(s_feat[t * 8 + i], __ldg(w + OFF_TOF_WT + i * 256 + tid), v);
-      v += s_part[t * 256 + tid] + s_part[(4 + t) * 256 + tid];
-      s_te[t * 256 + tid] = v;
-      sm += v;
-      mx = fmaxf(mx, v);
-    }
-    s_q[tid] = nmean + sm / (float)K;
-    s_q[256 + tid] = nmax + mx;
     if (SPLIT) {
-      // split decoder: the query (policy.py:179-182) and the tour embeddings go to HBM; the dense stages (ctxt_proj,
-      // glimpse keys / values, logit keys) run as tcgen05 GEMMs over 128 rollouts in decoder_tc.cu
-      st.dq[(size_t)b * 512 + tid] = s_q[tid];
-      st.dq[(size_t)b * 512 + 256 + tid] = s_q[256 + tid];
-      for (int t = 0; t < K; ++t) st.dte[((size_t)b * 4 + t) * 256 + tid] = s_te[t * 256 + tid];
+      // split decoder: the column statistics, the per-tour means of h and the tour features go to HBM; the tour
+      // embeddings (tour_encoder.py:202-213), the query (policy.py:179-182) and everything after them are computed by
+      // decoder_tc.cu for 128 rollouts at a time (dq / dqp are its scratch rows of this rollout)
+      st.dq[(size_t)b * 512 + tid] = nmean;
+      st.dq[(size_t)b * 512 + 256 + tid] = nmax;
+      for (int e = tid; e < K * 128; e += P2_THREADS) st.dqp[((size_t)b * 4 + (e >> 7)) * 256 + (e & 127)] = s_mean[e];
+      if (tid < K * 8) st.dqp[((size_t)b * 4 + (tid >> 3)) * 256 + 128 + (tid & 7)] = s_feat[tid];
+    } else {
+      float sm = 0.0f, mx = -INFINITY;
+      for (int t = 0; t < K; ++t) {
+        float v = __ldg(w + OFF_TOF_B + tid);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v = fmaf(s_feat[t * 8 + i], __ldg(w + OFF_TOF_WT + i * 256 + tid), v);
+        v += s_part[t * 256 + tid] + s_part[(4 + t) * 256 + tid];
+        s_te[t * 256 + tid] = v;
+        sm += v;
+        mx = fmaxf(mx, v);
+      }
+      s_q[tid] = nmean + sm / (float)K;
+      s_q[256 + tid] = nmax + mx;
     }
   }
   if (SPLIT) {

@@ -139,6 +139,7 @@ def pack_tc(sd: Dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16) ->
     mats += [sp[64 * h:64 * h + 64, :].t().contiguous() for h in range(4)]                 # (256, 64) per head: qp_h = B ctxt_h
     mats += [sp[256 + 64 * h:256 + 64 * h + 64, :].contiguous() for h in range(4)]         # (64, 256) per head: 4 tiles each
     mats += [m1]                                                                           # (256, 256): 4 tiles
+    mats += [sd["tour_encoder.output_proj.weight"][:, 128:].contiguous()]                  # (256, 128): 2 tiles, tour_emb
     hi = [m.to(dtype) for m in mats]
     lo = [(m - h_.float()).to(dtype) for m, h_ in zip(mats, hi)]
     for part in (hi, lo):
