@@ -512,13 +512,16 @@ def main():
         if env_roof is not None:
             roof["secondary"] = env_roof
         if dec_evs:
-            # the decoder launch against the HBM roofline.  Algorithmic bytes per rollout and step (A*D*s
-            # for the candidate rows once, "fused behind set_proj") + the hand-over vectors between its stages
-            # (q 2 KB, tour embeddings 3 KB, qp / gbar 4 KB each written + read, lp 1 KB written + read)
+            # the decoder launch against the HBM roofline.  Algorithmic bytes per rollout and step = what the launch must
+            # read and write whatever its organisation (decoder tail "fused behind set_proj"): the candidate
+            # rows A*D*s once, the node statistics 2*D*4, the per-tour means and features K*(128+8)*4, candidate ids and
+            # masks 3*A, the decision 24 B.  Its hand-over vectors between stages (q, tour embeddings, qp, gbar, lp:
+            # ~40 KB per rollout written and re-read, mostly through L2) are implementation traffic: see `traffic`.
             live_dec = [m.elapsed_time(b) for i, (m, (_, b)) in enumerate(zip(dec_evs, evs)) if env._step + i <= done2]
             live_gnn = [a.elapsed_time(m) for i, (m, (a, _)) in enumerate(zip(dec_evs, evs)) if env._step + i <= done2]
             dec_ms = float(np.mean(live_dec))
-            dec_bytes = (A_act * 256 * 2 + 2048 + 3072 + 2 * 4096 + 2 * 4096 + 2 * 1024) * bs
+            Kv = ENV_KW["max_concurrent_vehicles"]
+            dec_bytes = (A_act * 256 * 2 + 2 * 256 * 4 + Kv * (128 + 8) * 4 + 3 * A_act + 24) * bs
             hbm = float(peaks.get("hbm_gbs", 6650.0))
             dtr = tr.get("per_kernel", {}).get("decoder_tc_kernel") if traffic is not None else None
             roof["decoder"] = {"bound": "hbm", "kernel": "decoder_tc_kernel (second launch of the policy step)",
