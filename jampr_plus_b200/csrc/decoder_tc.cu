@@ -7,7 +7,7 @@
 //   stage A   ctxt = q W_c^T                       GEMM 128 x 256 x 512          (attn_decoder.py:73)
 //   stage B   qp_h = W_gk,h^T ctxt_h  (4 heads)    4 GEMMs 128 x 256 x 64        (set_proj moved to the query side)
 //   phase C   per rollout, one warp: glimpse scores qp_h . (node_emb[n_a] + tour_emb[t_a]) over the FEASIBLE actions,
-//             masked softmax per head, gbar_h = sum_a p_h[a] act[a]
+//             masked softmax per head, gbar_h = sum_a p_h[a] act[a] — on warp-level tensor-core MMAs (see below)
 //   stage D   g[64h..] = W_gv,h gbar_h  (4 heads)  4 GEMMs 128 x 64 x 256        (attn_decoder.py:86-88)
 //   stage E   lp = (W_lk^T W_out) g                GEMM 128 x 256 x 256          (out_proj + logit keys, pre-multiplied)
 //   phase F   per rollout, one warp: logits 10 tanh(lp . act[a] / 16), masked log-softmax, greedy argmax or
@@ -21,14 +21,26 @@
 // (the fused per-rollout decoder streamed 704 KB of them per rollout).
 // A operand tiles are written by the threads (from HBM vectors or straight from the previous accumulator in TMEM),
 // B tiles are pre-swizzled images streamed by the bulk-copy engine into a double buffer, one item ahead.
+//
+// The per-rollout phases C and F are the HBM-facing part: each gathers the 16-bit node-embedding rows of the feasible
+// actions (512 B per row, ~2.7 GB per launch at 65,536 rollouts).  A warp stages 16 rows at a time in shared memory
+// with 16-byte asynchronous copies (no register staging: 8 KB in flight per warp, 128 KB per SM) and runs the dot
+// products as mma.sync.m16n8k16 on fragments read with ldmatrix:
+//   scores   S[h][a]  = sum_c Qp[h][c] R[a][c]     A = Qp as [hi(4 heads); lo(4 heads)] (fp32 = hi + lo), B = R
+//   glimpse  G[c][h] += sum_a R[a][c] P[a][h]      A = R^T (ldmatrix.trans), B = [hi(p); lo(p)] straight from the score
+//                                                  accumulators (flash-attention register reuse), online softmax
+// so the rows are fetched once for scores and weighted sums, and a rollout costs ~2.5 k instructions instead of
+// ~12 k on the CUDA cores.  Node-embedding rows are exact 16-bit values; queries and probabilities enter as hi + lo,
+// products are exact and accumulate in fp32: the accuracy of the fp32 dot products it replaces.
 #include <stdlib.h>
 #include "policy_tc_common.cuh"
 
 #define DT_THREADS 512
 #define DT_WARPS (DT_THREADS / 32)
 #define DT_M 128
-#define DT_BATCH 8             // node-embedding rows in flight per lane in the per-rollout passes
-#define DT_BATCH3 16           // same in the logit pass, which keeps few other registers live
+#define DT_RROWS 16            // node-embedding rows staged per chunk (two mma n-tiles)
+#define DT_RSTRIDE 528         // bytes per staged row: 512 + 16 (8 consecutive rows hit 32 distinct banks in ldmatrix)
+#define DT_GSTRIDE 260         // floats per row of the [8][256] hand-over of the glimpse accumulators (conflict-free)
 #define DT_ITEMS 32            // B tiles consumed after stage T (2 per vehicle slot): 8 (stage A) + 4 (B) + 16 (D) + 4 (E)
 
 struct DtArgs {
@@ -82,8 +94,17 @@ __device__ __forceinline__ void dt_item_src(int i, int n_t, uint32_t& off, uint3
 }
 
 __host__ __device__ inline uint32_t dt_a32(int A) { return (uint32_t)(A + 31) & ~31u; }
-// per-warp scratch: probabilities [A32][4] f32 | logits [A32] f32 | feasible list [A32] i16 | nodes [A32] i16 | qt [16] f32
-__host__ __device__ inline uint32_t dt_warp_bytes(int A) { return dt_a32(A) * (16 + 4 + 2 + 2) + 64; }
+// per-warp scratch: staged rows [16][528 B] | query rows [8][528 B] (hi of 4 vectors, lo of 4 vectors) | logits [A32] f32 |
+// feasible list [A32] i16 | nodes [A32] i16 | qt [16] f32.  The warps' regions overlay the GEMM operand tiles (dead
+// during the per-rollout phases).
+#define DT_R_BYTES (DT_RROWS * DT_RSTRIDE)
+#define DT_Q_BYTES (8 * DT_RSTRIDE)
+__host__ __device__ inline uint32_t dt_warp_bytes(int A) { return DT_R_BYTES + DT_Q_BYTES + dt_a32(A) * (4 + 2 + 2) + 64; }
+#define DT_GEMM_BYTES (32768u + 131072u)
+__host__ __device__ inline uint32_t dt_region_bytes(int A) {
+  const uint32_t w = DT_WARPS * dt_warp_bytes(A);
+  return w > DT_GEMM_BYTES ? w : DT_GEMM_BYTES;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs a) {
@@ -98,20 +119,22 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t A32 = dt_a32(A);
 
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // pointer arithmetic keeps the shared space
   uint8_t* sAhi = base;                    // [128 rows][64 K] hi
   uint8_t* sAlo = base + 16384;            // lo
   uint8_t* sB = base + 32768;              // 2 buffers x (hi 32 KB | lo 32 KB)
-  uint8_t* scratch = base + 32768 + 131072;
+  uint8_t* scratch = base + dt_region_bytes(A);
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch);          // full[0], full[1], mma
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(scratch + 32);
   int* s_any = reinterpret_cast<int*>(scratch + 48);
-  uint8_t* wbase = scratch + 64 + (size_t)warp * dt_warp_bytes(A);
-  float* s_p = reinterpret_cast<float*>(wbase);                               // [A32][4]
-  float* s_logit = reinterpret_cast<float*>(wbase + A32 * 16);                // [A32]
-  int16_t* s_list = reinterpret_cast<int16_t*>(wbase + A32 * 20);             // feasible action indices
-  int16_t* s_nb = reinterpret_cast<int16_t*>(wbase + A32 * 22);               // node of action a
-  float* s_qt = reinterpret_cast<float*>(wbase + A32 * 24);                   // [4 heads][4 slots]
+  // per-warp region of the per-rollout phases (over the operand tiles)
+  uint8_t* wbase = base + (size_t)warp * dt_warp_bytes(A);
+  uint8_t* sR = wbase;                                                        // staged rows | glimpse hand-over
+  uint8_t* sQ = wbase + DT_R_BYTES;                                           // query rows: hi 0..3, lo 4..7
+  float* s_logit = reinterpret_cast<float*>(wbase + DT_R_BYTES + DT_Q_BYTES); // [A32]
+  int16_t* s_list = reinterpret_cast<int16_t*>(wbase + DT_R_BYTES + DT_Q_BYTES + A32 * 4);      // feasible action indices
+  int16_t* s_nb = reinterpret_cast<int16_t*>(wbase + DT_R_BYTES + DT_Q_BYTES + A32 * 6);        // node of action a
+  float* s_qt = reinterpret_cast<float*>(wbase + DT_R_BYTES + DT_Q_BYTES + A32 * 8);            // [4 heads][4 slots]
   uint64_t* full = bars;
   uint64_t* bar_mma = bars + 2;
 
@@ -209,7 +232,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   };
   // one item, first half: the A tile is filled; issue the next B load, wait for this one, 12 MMAs (4 K steps x hi*hi,
   // lo*hi, hi*lo), commit.  Second half: every thread waits for the MMAs (A tile and accumulator free / valid).
-  auto issue_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first) {
+  auto issue_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first, bool prefetch = true) {
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -227,15 +250,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
         umma_f16(tmem + d_col, dah, dbl, idesc, 1u);
       }
       umma_commit(bar_mma);
-      if (i + 1 < n_items) issue_b(i + 1);           // off the critical path; its buffer was last read by item i - 1 (complete)
+      if (prefetch && i + 1 < n_items) issue_b(i + 1);     // off the critical path; its buffer was last read by item i - 1 (complete)
     }
   };
   auto wait_item = [&](int i) {
     mbar_wait(bar_mma, (uint32_t)(i & 1));
     tc_fence_after();
   };
-  auto run_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first) {
-    issue_item(i, d_col, idesc, first);
+  auto run_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first, bool prefetch = true) {
+    issue_item(i, d_col, idesc, first, prefetch);
     wait_item(i);
   };
 
@@ -336,7 +359,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
 #pragma unroll 1
   for (int h = 0; h < 4; ++h) {
     fill_from_tmem((uint32_t)h * 64u);
-    run_item(n_t + 8 + h, 256u, idesc256, true);
+    run_item(n_t + 8 + h, 256u, idesc256, true, h < 3);      // no B tile in flight during phase C: it overlays the buffers
     drain_to_global(256u, st.dqp + (size_t)h * 256, 1024);
     tc_fence_before();           // the next item's MMAs overwrite these columns after the block barrier in run_item
   }
@@ -346,12 +369,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
 
   // ================================================================ phase C: glimpse per rollout (one warp each)
   const T* ne16 = reinterpret_cast<const T*>(st.ne16);
-#pragma unroll 1
-  for (int rr = warp; rr < DT_M; rr += DT_WARPS) {
-    const int b = b0 + rr;
-    if (b >= bs) break;
-    if (jampr_rollout_idle(st, b, K)) continue;
-    // feasible actions in ascending order
+  const int g8 = lane >> 2, t4 = lane & 3;            // mma fragment coordinates
+  const uint32_t r_saddr = smem_u32(sR), q_saddr = smem_u32(sQ);
+  // ldmatrix row addresses of this lane: staged rows as four 8x8 blocks (rows 0-7 | 8-15) x (columns 0-7 | 8-15) of a
+  // 16-column step, query rows as two blocks (columns 0-7 | 8-15)
+  const uint32_t r_lm = r_saddr + (uint32_t)(((lane >> 4) << 3) + (lane & 7)) * DT_RSTRIDE + (uint32_t)((lane >> 3) & 1) * 16u;
+  const uint32_t q_lm = q_saddr + (uint32_t)(lane & 7) * DT_RSTRIDE + (uint32_t)((lane >> 3) & 1) * 16u;
+  // feasible actions of rollout b in ascending order -> s_list (action | slot << 10), s_nb; returns their number
+  auto build_list = [&](int b, bool init_logits) {
     int cnt = 0;
     for (int e0 = 0; e0 < A; e0 += 32) {
       const int e = e0 + lane;
@@ -359,11 +384,67 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       if (e < A) {
         s_nb[e] = st.nbh[(size_t)b * A + e];
         ok = st.mask[(size_t)b * A + e] == 0;
+        if (init_logits) s_logit[e] = -INFINITY;
       }
       const unsigned m = __ballot_sync(0xffffffffu, ok);
       if (ok) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (int16_t)(e | ((e / k) << 10));      // action | slot << 10
       cnt += __popc(m);
     }
+    __syncwarp();
+    return cnt;
+  };
+  // rows of the feasible actions i0 .. i0+15 -> sR (rows past the end are zero-filled: they enter the glimpse MMA with
+  // weight 0 and must be finite)
+  auto stage_rows = [&](const uint8_t* rows_b, int i0, int cnt) {
+    int goff = 0;
+    if (lane < DT_RROWS) goff = (int)s_nb[s_list[min(i0 + lane, cnt - 1)] & 1023] * 512;
+#pragma unroll
+    for (int r = 0; r < DT_RROWS; ++r) {
+      const int off = __shfl_sync(0xffffffffu, goff, r);
+      const uint32_t nbytes = (i0 + r < cnt) ? 16u : 0u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(r_saddr + (uint32_t)r * DT_RSTRIDE + (uint32_t)lane * 16u),
+                   "l"(rows_b + off), "r"(nbytes)
+                   : "memory");
+    }
+    cp_async_wait_all();
+    __syncwarp();
+  };
+  // S[v][a] = sum_c Q[v][c] R[a][c] for the 16 staged rows: this lane ends up with the full dot products (hi + lo) of
+  // query vector g8 & 3 for the chunk positions 2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4
+  auto chunk_scores = [&](float (&sc)[4]) {
+    float acc0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+    for (int ks = 0; ks < 16; ++ks) {
+      uint32_t b00, b01, b10, b11, a0, a2;
+      ldsm_x4(r_lm + (uint32_t)ks * 32u, b00, b01, b10, b11);
+      ldsm_x2(q_lm + (uint32_t)ks * 32u, a0, a2);
+      mma16816<T>(acc0, a0, 0u, a2, 0u, b00, b01);
+      mma16816<T>(acc1, a0, 0u, a2, 0u, b10, b11);
+    }
+    sc[0] = acc0[0] + __shfl_xor_sync(0xffffffffu, acc0[0], 16);
+    sc[1] = acc0[1] + __shfl_xor_sync(0xffffffffu, acc0[1], 16);
+    sc[2] = acc1[0] + __shfl_xor_sync(0xffffffffu, acc1[0], 16);
+    sc[3] = acc1[1] + __shfl_xor_sync(0xffffffffu, acc1[1], 16);
+  };
+  // fp32 vector (this lane's 8 columns) -> query rows `row` (hi) and 4 + `row` (lo)
+  auto put_query = [&](int row, const float2 (&v)[4]) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const T2 hh = Elem<T>::from2(v[i].x, v[i].y);
+      const float2 hf = Elem<T>::to2(hh);
+      hi[i] = as_u32(hh);
+      lo[i] = as_u32(Elem<T>::from2(v[i].x - hf.x, v[i].y - hf.y));
+    }
+    *reinterpret_cast<uint4*>(sQ + (size_t)row * DT_RSTRIDE + lane * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(sQ + (size_t)(4 + row) * DT_RSTRIDE + lane * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  };
+#pragma unroll 1
+  for (int rr = warp; rr < DT_M; rr += DT_WARPS) {
+    const int b = b0 + rr;
+    if (b >= bs) break;
+    if (jampr_rollout_idle(st, b, K)) continue;
+    const int cnt = build_list(b, false);
     // per-head glimpse query: lane owns columns 8 lane .. 8 lane + 7
     float2 qv[4][4];
 #pragma unroll
@@ -389,121 +470,140 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       const float z = warp_sum4(dd[0], dd[1], dd[2], dd[3], lane);
       if ((lane & 7) == 0) s_qt[(((lane >> 4) << 1) | ((lane >> 3) & 1)) * 4 + t] = z;
     }
+#pragma unroll
+    for (int h = 0; h < 4; ++h) put_query(h, qv[h]);
     __syncwarp();
-    // pass 1: scores of the feasible actions.  The rows come from HBM / L2 (~1 us): DT_BATCH independent 16-byte loads
-    // per lane are issued back to back before the first is consumed (Little: ~30 KB in flight per SM are needed)
-    const T* rows = ne16 + (size_t)b * N * 256 + lane * 8;
+    // this lane's head in the score fragments, its tour terms qp_h . tour_emb[t]
+    const int hh = g8 & 3;
+    float qt_r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) qt_r[q] = (q < K) ? s_qt[hh * 4 + q] : 0.0f;
+    const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(ne16 + (size_t)b * N * 256) + lane * 16;
+    // online softmax over the chunks: running maximum m_run, this lane's partial denominator l_part and per-slot
+    // partial weight sums ps[] (all relative to m_run), glimpse accumulators G[c][v] (v < 4: hi of p, v >= 4: lo of p)
+    float m_run = -INFINITY, l_part = 0.0f, ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float G[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { G[i][0] = 0.0f; G[i][1] = 0.0f; G[i][2] = 0.0f; G[i][3] = 0.0f; }
 #pragma unroll 1
-    for (int i0 = 0; i0 < cnt; i0 += DT_BATCH) {
-      uint4 raw[DT_BATCH];
-      int ee[DT_BATCH];
+    for (int i0 = 0; i0 < cnt; i0 += DT_RROWS) {
+      stage_rows(rows_b, i0, cnt);
+      float sc[4];
+      chunk_scores(sc);
+      const uint32_t lwA = *reinterpret_cast<const uint32_t*>(s_list + i0 + 2 * t4);
+      const uint32_t lwB = *reinterpret_cast<const uint32_t*>(s_list + i0 + 8 + 2 * t4);
+      const int slot[4] = {(int)((lwA >> 10) & 63u), (int)(lwA >> 26), (int)((lwB >> 10) & 63u), (int)(lwB >> 26)};
+      const int pos0 = i0 + 2 * t4;
+      const bool ok[4] = {pos0 < cnt, pos0 + 1 < cnt, pos0 + 8 < cnt, pos0 + 9 < cnt};
+      float mloc = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < DT_BATCH; ++j) {
-        const int i = min(i0 + j, cnt - 1);
-        ee[j] = s_list[i];
-        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[ee[j] & 1023] * 256);
+      for (int j = 0; j < 4; ++j) {
+        const float qt = (slot[j] == 0) ? qt_r[0] : (slot[j] == 1) ? qt_r[1] : (slot[j] == 2) ? qt_r[2] : qt_r[3];
+        sc[j] = ok[j] ? (sc[j] + qt) * 0.125f : -INFINITY;
+        mloc = fmaxf(mloc, sc[j]);
+      }
+      mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 1));
+      mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 2));
+      const float m_new = fmaxf(m_run, mloc);             // finite: position i0 of the chunk is valid
+      const float rs = expf(m_run - m_new);               // first chunk: exp(-inf) = 0
+      m_run = m_new;
+      float pj[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pj[j] = expf(sc[j] - m_new);
+      l_part = fmaf(l_part, rs, (pj[0] + pj[1]) + (pj[2] + pj[3]));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float add = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) add += (slot[j] == q) ? pj[j] : 0.0f;
+        ps[q] = fmaf(ps[q], rs, add);
+      }
+      // probabilities as the B operand: lanes with g8 < 4 carry the hi parts, the others the lo parts
+      const T2 h0 = Elem<T>::from2(pj[0], pj[1]), h1 = Elem<T>::from2(pj[2], pj[3]);
+      const float2 f0 = Elem<T>::to2(h0), f1 = Elem<T>::to2(h1);
+      const T2 l0 = Elem<T>::from2(pj[0] - f0.x, pj[1] - f0.y), l1 = Elem<T>::from2(pj[2] - f1.x, pj[3] - f1.y);
+      const uint32_t pb0 = (g8 < 4) ? as_u32(h0) : as_u32(l0), pb1 = (g8 < 4) ? as_u32(h1) : as_u32(l1);
+      // rescale the accumulators: this lane's columns belong to heads (2 t4) & 3 and (2 t4 + 1) & 3
+      const int ha = (2 * t4) & 3;
+      const float rsa = __shfl_sync(0xffffffffu, rs, 4 * ha), rsb = __shfl_sync(0xffffffffu, rs, 4 * ha + 4);
+      if (!__all_sync(0xffffffffu, rs == 1.0f)) {
+        const float2 r2 = make_float2(rsa, rsb);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 u = __fmul2_rn(make_float2(G[i][0], G[i][1]), r2), v = __fmul2_rn(make_float2(G[i][2], G[i][3]), r2);
+          G[i][0] = u.x; G[i][1] = u.y; G[i][2] = v.x; G[i][3] = v.y;
+        }
       }
 #pragma unroll
-      for (int j = 0; j < DT_BATCH; ++j) {
-        const float2 v0 = Elem<T>::to2(from_u32<T2>(raw[j].x)), v1 = Elem<T>::to2(from_u32<T2>(raw[j].y));
-        const float2 v2 = Elem<T>::to2(from_u32<T2>(raw[j].z)), v3 = Elem<T>::to2(from_u32<T2>(raw[j].w));
-        float dd[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          float2 acc = __ffma2_rn(v0, qv[h][0], make_float2(0.0f, 0.0f));
-          acc = __ffma2_rn(v1, qv[h][1], acc);
-          acc = __ffma2_rn(v2, qv[h][2], acc);
-          acc = __ffma2_rn(v3, qv[h][3], acc);
-          dd[h] = acc.x + acc.y;
-        }
-        const float z = warp_sum4(dd[0], dd[1], dd[2], dd[3], lane);
-        if ((lane & 7) == 0 && i0 + j < cnt) {
-          const int h = ((lane >> 4) << 1) | ((lane >> 3) & 1);
-          s_p[(i0 + j) * 4 + h] = (z + s_qt[h * 4 + (ee[j] >> 10)]) * 0.125f;
-        }
+      for (int i = 0; i < 16; ++i) {
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4_t(r_lm + (uint32_t)i * 32u, a0, a1, a2, a3);
+        mma16816<T>(G[i], a0, a1, a2, a3, pb0, pb1);
       }
+      __syncwarp();
     }
-    __syncwarp();
-    // softmax per head over the feasible actions (masked actions have weight 0)
+    // denominators and slot weights of this lane's head
+    l_part += __shfl_xor_sync(0xffffffffu, l_part, 1);
+    l_part += __shfl_xor_sync(0xffffffffu, l_part, 2);
+    const float inv = 1.0f / l_part;
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      float mx = -INFINITY;
-      for (int i = lane; i < cnt; i += 32) mx = fmaxf(mx, s_p[i * 4 + h]);
-      mx = warp_max(mx);
-      float sum = 0.0f;
-      for (int i = lane; i < cnt; i += 32) {
-        const float ex = expf(s_p[i * 4 + h] - mx);
-        s_p[i * 4 + h] = ex;
-        sum += ex;
-      }
-      sum = warp_sum(sum);
-      for (int i = lane; i < cnt; i += 32) s_p[i * 4 + h] = s_p[i * 4 + h] / sum;
+    for (int q = 0; q < 4; ++q) {
+      ps[q] += __shfl_xor_sync(0xffffffffu, ps[q], 1);
+      ps[q] += __shfl_xor_sync(0xffffffffu, ps[q], 2);
+      ps[q] *= inv;
     }
-    __syncwarp();
-    // pass 2: gbar_h = sum_a p_h[a] (node_emb[n_a] + tour_emb[t_a])
-    float2 g[4][4];
+    // accumulators -> [8][256] fp32 in the (dead) row buffer, then per lane 8 columns x 4 heads:
+    // gbar_h = (hi + lo) / denominator + sum_t P_h[t] tour_emb[t]
+    {
+      float* sG = reinterpret_cast<float*>(sR);
 #pragma unroll
-    for (int h = 0; h < 4; ++h)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) g[h][j] = make_float2(0.0f, 0.0f);
-    const uint32_t p_saddr = smem_u32(s_p);
-    // tour-embedding part first: gbar_h += P_h[t] tour_emb[t], P_h[t] = sum of p_h over the actions of slot t
-    for (int t = 0; t < K; ++t) {
-      float ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      for (int i = lane; i < cnt; i += 32) {
-        if ((s_list[i] >> 10) == t) {
-          const float4 pw = lds_f32x4(p_saddr + (uint32_t)i * 16u);
-          ps[0] += pw.x; ps[1] += pw.y; ps[2] += pw.z; ps[3] += pw.w;
-        }
+      for (int i = 0; i < 16; ++i) {
+        sG[(2 * t4) * DT_GSTRIDE + 16 * i + g8] = G[i][0];
+        sG[(2 * t4 + 1) * DT_GSTRIDE + 16 * i + g8] = G[i][1];
+        sG[(2 * t4) * DT_GSTRIDE + 16 * i + g8 + 8] = G[i][2];
+        sG[(2 * t4 + 1) * DT_GSTRIDE + 16 * i + g8 + 8] = G[i][3];
       }
-      const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
-      const float4 x = p[0], y = p[1];
-      const float2 t0 = make_float2(x.x, x.y), t1 = make_float2(x.z, x.w), t2 = make_float2(y.x, y.y), t3 = make_float2(y.z, y.w);
+      __syncwarp();
+      float2 gb[4][4];
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const float2 p2 = f2(warp_sum(ps[h]));
-        g[h][0] = __ffma2_rn(p2, t0, g[h][0]);
-        g[h][1] = __ffma2_rn(p2, t1, g[h][1]);
-        g[h][2] = __ffma2_rn(p2, t2, g[h][2]);
-        g[h][3] = __ffma2_rn(p2, t3, g[h][3]);
+        const float ih = __shfl_sync(0xffffffffu, inv, 4 * h);
+        const float4 x = *reinterpret_cast<const float4*>(sG + h * DT_GSTRIDE + lane * 8);
+        const float4 y = *reinterpret_cast<const float4*>(sG + h * DT_GSTRIDE + lane * 8 + 4);
+        const float4 u = *reinterpret_cast<const float4*>(sG + (4 + h) * DT_GSTRIDE + lane * 8);
+        const float4 v = *reinterpret_cast<const float4*>(sG + (4 + h) * DT_GSTRIDE + lane * 8 + 4);
+        gb[h][0] = make_float2((x.x + u.x) * ih, (x.y + u.y) * ih);
+        gb[h][1] = make_float2((x.z + u.z) * ih, (x.w + u.w) * ih);
+        gb[h][2] = make_float2((y.x + v.x) * ih, (y.y + v.y) * ih);
+        gb[h][3] = make_float2((y.z + v.z) * ih, (y.w + v.w) * ih);
       }
-    }
-#pragma unroll 1
-    for (int i0 = 0; i0 < cnt; i0 += DT_BATCH) {
-      uint4 raw[DT_BATCH];
+      for (int t = 0; t < K; ++t) {
+        const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
+        const float4 x = p[0], y = p[1];
+        const float2 t0 = make_float2(x.x, x.y), t1 = make_float2(x.z, x.w), t2 = make_float2(y.x, y.y), t3 = make_float2(y.z, y.w);
+        const float pst = (t == 0) ? ps[0] : (t == 1) ? ps[1] : (t == 2) ? ps[2] : ps[3];
 #pragma unroll
-      for (int j = 0; j < DT_BATCH; ++j) {
-        const int i = min(i0 + j, cnt - 1);
-        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[s_list[i] & 1023] * 256);
-      }
-#pragma unroll
-      for (int j = 0; j < DT_BATCH; ++j) {
-        if (i0 + j < cnt) {        // warp-uniform
-          const float2 v0 = Elem<T>::to2(from_u32<T2>(raw[j].x)), v1 = Elem<T>::to2(from_u32<T2>(raw[j].y));
-          const float2 v2 = Elem<T>::to2(from_u32<T2>(raw[j].z)), v3 = Elem<T>::to2(from_u32<T2>(raw[j].w));
-          const float4 pw = lds_f32x4(p_saddr + (uint32_t)(i0 + j) * 16u);
-          const float ph[4] = {pw.x, pw.y, pw.z, pw.w};
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const float2 p2 = f2(ph[h]);
-            g[h][0] = __ffma2_rn(p2, v0, g[h][0]);
-            g[h][1] = __ffma2_rn(p2, v1, g[h][1]);
-            g[h][2] = __ffma2_rn(p2, v2, g[h][2]);
-            g[h][3] = __ffma2_rn(p2, v3, g[h][3]);
-          }
+        for (int h = 0; h < 4; ++h) {
+          const float2 p2 = f2(__shfl_sync(0xffffffffu, pst, 4 * h));
+          gb[h][0] = __ffma2_rn(p2, t0, gb[h][0]);
+          gb[h][1] = __ffma2_rn(p2, t1, gb[h][1]);
+          gb[h][2] = __ffma2_rn(p2, t2, gb[h][2]);
+          gb[h][3] = __ffma2_rn(p2, t3, gb[h][3]);
         }
       }
-    }
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      float4* o = reinterpret_cast<float4*>(st.dgbar + ((size_t)b * 4 + h) * 256 + lane * 8);
-      o[0] = make_float4(g[h][0].x, g[h][0].y, g[h][1].x, g[h][1].y);
-      o[1] = make_float4(g[h][2].x, g[h][2].y, g[h][3].x, g[h][3].y);
+      for (int h = 0; h < 4; ++h) {
+        float4* o = reinterpret_cast<float4*>(st.dgbar + ((size_t)b * 4 + h) * 256 + lane * 8);
+        o[0] = make_float4(gb[h][0].x, gb[h][0].y, gb[h][1].x, gb[h][1].y);
+        o[1] = make_float4(gb[h][2].x, gb[h][2].y, gb[h][3].x, gb[h][3].y);
+      }
     }
     __syncwarp();
   }
+  fence_proxy_async();           // the warps' generic-proxy writes over the operand tiles precede the next bulk copies
   __threadfence_block();
   __syncthreads();
+  if (tid == 0) issue_b(n_t + 12);
 
   // ================================================================ stage D: g (TMEM columns 0..255, 64 per head)
   {
@@ -547,19 +647,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       }
       continue;
     }
-    int cnt = 0;
-    for (int e0 = 0; e0 < A; e0 += 32) {
-      const int e = e0 + lane;
-      bool ok = false;
-      if (e < A) {
-        s_nb[e] = st.nbh[(size_t)b * A + e];
-        ok = st.mask[(size_t)b * A + e] == 0;
-        s_logit[e] = -INFINITY;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (ok) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (int16_t)(e | ((e / k) << 10));
-      cnt += __popc(m);
-    }
+    const int cnt = build_list(b, true);
     float2 lv[4];
     {
       const float4* p = reinterpret_cast<const float4*>(st.dlp + (size_t)b * 256 + lane * 8);
@@ -579,29 +667,25 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       for (int j = 0; j < 4; ++j)
         if (j == t) lt[j] = z;
     }
+    // logit vector as query row 0 (hi) / 4 (lo); the other query rows keep finite leftovers of phase C or zeros, and
+    // rows of the score MMA are independent
+    put_query(0, lv);
     __syncwarp();
-    const T* rows = ne16 + (size_t)b * N * 256 + lane * 8;
+    const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(ne16 + (size_t)b * N * 256) + lane * 16;
 #pragma unroll 1
-    for (int i0 = 0; i0 < cnt; i0 += DT_BATCH3) {
-      uint4 raw[DT_BATCH3];
-      int ee[DT_BATCH3];
-#pragma unroll
-      for (int j = 0; j < DT_BATCH3; ++j) {
-        const int i = min(i0 + j, cnt - 1);
-        ee[j] = s_list[i];
-        raw[j] = *reinterpret_cast<const uint4*>(rows + (size_t)s_nb[ee[j] & 1023] * 256);
+    for (int i0 = 0; i0 < cnt; i0 += DT_RROWS) {
+      stage_rows(rows_b, i0, cnt);
+      float sc[4];
+      chunk_scores(sc);
+      if (g8 == 0) {          // raw dot products; the clip follows, vectorised
+        const int pos0 = i0 + 2 * t4;
+        if (pos0 < cnt) s_logit[s_list[pos0] & 1023] = sc[0];
+        if (pos0 + 1 < cnt) s_logit[s_list[pos0 + 1] & 1023] = sc[1];
+        if (pos0 + 8 < cnt) s_logit[s_list[pos0 + 8] & 1023] = sc[2];
+        if (pos0 + 9 < cnt) s_logit[s_list[pos0 + 9] & 1023] = sc[3];
       }
-#pragma unroll
-      for (int j = 0; j < DT_BATCH3; ++j) {
-        float2 acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].x)), lv[0], make_float2(0.0f, 0.0f));
-        acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].y)), lv[1], acc);
-        acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].z)), lv[2], acc);
-        acc = __ffma2_rn(Elem<T>::to2(from_u32<T2>(raw[j].w)), lv[3], acc);
-        const float z = warp_sum(acc.x + acc.y);
-        if (lane == 0 && i0 + j < cnt) s_logit[ee[j] & 1023] = z;          // raw dot product; the clip follows, vectorised
-      }
+      __syncwarp();
     }
-    __syncwarp();
     for (int i = lane; i < cnt; i += 32) {
       const int v = s_list[i], e = v & 1023, t = v >> 10;
       const float ltv = (t == 0) ? lt[0] : (t == 1) ? lt[1] : (t == 2) ? lt[2] : lt[3];
@@ -676,9 +760,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   }
 }
 
-static size_t dt_smem_bytes(const jampr_dims_t* d) {
-  return 1024 + 32768 + 131072 + 64 + (size_t)DT_WARPS * dt_warp_bytes(d->n_slots * d->k_nbh);
-}
+static size_t dt_smem_bytes(const jampr_dims_t* d) { return 1024 + (size_t)dt_region_bytes(d->n_slots * d->k_nbh) + 64; }
 
 template <typename T>
 static int launch_dt(const DtArgs& a, size_t smem, cudaStream_t s) {
