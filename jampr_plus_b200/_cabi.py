@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libjampr_b200.so")
+# JAMPR_B200_LIB selects an instrumented side build of the same library (csrc/Makefile VARIANT=...; profiling tools only)
+LIB_PATH = os.environ.get("JAMPR_B200_LIB") or os.path.join(_HERE, "lib", "libjampr_b200.so")
 
 ABI_VERSION = 4
 ST_NO_FEASIBLE, ST_TOUR_OVERFLOW, ST_FLEET_EXHAUSTED, ST_NAN_LOGITS, ST_TW_COLLAPSE = 1, 2, 4, 8, 16

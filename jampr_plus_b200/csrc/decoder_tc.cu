@@ -43,6 +43,15 @@
 #define DT_GSTRIDE 260         // floats per row of the [8][256] hand-over of the glimpse accumulators (conflict-free)
 #define DT_ITEMS 32            // B tiles consumed after stage T (2 per vehicle slot): 8 (stage A) + 4 (B) + 16 (D) + 4 (E)
 
+// per-phase time line of the CTAs (tools/timeline.py decoder): build with `make EXTRA=-DJAMPR_TIMELINE`
+#ifdef JAMPR_TIMELINE
+#define DTL_N 16
+__device__ uint32_t g_dtimeline[1024][DTL_N];
+#define DTL(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_dtimeline[blockIdx.x][k] = (uint32_t)clock64(); } while (0)
+#else
+#define DTL(k) do { } while (0)
+#endif
+
 struct DtArgs {
   jampr_dims_t d;
   jampr_state_t st;
@@ -85,7 +94,7 @@ __device__ __forceinline__ void write_a16(uint8_t* sAhi, uint8_t* sAlo, int r, i
 
 // B tile of item i inside one part of the decoder blob: element offset and element count
 __device__ __forceinline__ void dt_item_src(int i, int n_t, uint32_t& off, uint32_t& elems) {
-  if (i < n_t) { off = WD_TO + (uint32_t)(i & 1) * WD_TILE; elems = WD_TILE; return; }      // stage T: (slot, K-block) items
+  if (i < n_t) { off = WD_TO + (uint32_t)(i % 3) * WD_TILE; elems = WD_TILE; return; }      // stage T: (slot, K-block) items
   i -= n_t;
   if (i < 8) { off = WD_C + (uint32_t)i * WD_TILE; elems = WD_TILE; }
   else if (i < 12) { off = WD_GK + (uint32_t)(i - 8) * WD_TILE; elems = WD_TILE; }
@@ -100,7 +109,7 @@ __host__ __device__ inline uint32_t dt_a32(int A) { return (uint32_t)(A + 31) & 
 #define DT_R_BYTES (DT_RROWS * DT_RSTRIDE)
 #define DT_Q_BYTES (8 * DT_RSTRIDE)
 __host__ __device__ inline uint32_t dt_warp_bytes(int A) { return DT_R_BYTES + DT_Q_BYTES + dt_a32(A) * (4 + 2 + 2) + 64; }
-#define DT_GEMM_BYTES (32768u + 131072u)
+#define DT_GEMM_BYTES (65536u + 131072u)
 __host__ __device__ inline uint32_t dt_region_bytes(int A) {
   const uint32_t w = DT_WARPS * dt_warp_bytes(A);
   return w > DT_GEMM_BYTES ? w : DT_GEMM_BYTES;
@@ -120,11 +129,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   const uint32_t A32 = dt_a32(A);
 
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // pointer arithmetic keeps the shared space
-  uint8_t* sAhi = base;                    // [128 rows][64 K] hi
-  uint8_t* sAlo = base + 16384;            // lo
-  uint8_t* sB = base + 32768;              // 2 buffers x (hi 32 KB | lo 32 KB)
+  uint8_t* sA = base;                      // 2 buffers x ([128 rows][64 K] hi 16 KB | lo 16 KB)
+  uint8_t* sB = base + 65536;              // 2 buffers x (hi 32 KB | lo 32 KB)
   uint8_t* scratch = base + dt_region_bytes(A);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch);          // full[0], full[1], mma
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch);          // full[0], full[1], mma[0], mma[1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(scratch + 32);
   int* s_any = reinterpret_cast<int*>(scratch + 48);
   // per-warp region of the per-rollout phases (over the operand tiles)
@@ -136,7 +144,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   int16_t* s_nb = reinterpret_cast<int16_t*>(wbase + DT_R_BYTES + DT_Q_BYTES + A32 * 6);        // node of action a
   float* s_qt = reinterpret_cast<float*>(wbase + DT_R_BYTES + DT_Q_BYTES + A32 * 8);            // [4 heads][4 slots]
   uint64_t* full = bars;
-  uint64_t* bar_mma = bars + 2;
+  uint64_t* bar_mma = bars + 2;            // [2]
 
   // ---- does any rollout of this tile need a decision?  (late in the episode whole tiles are idle)
   if (tid == 0) *s_any = 0;
@@ -158,9 +166,19 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     return;
   }
 
-  const int n_t = 2 * K, n_items = n_t + DT_ITEMS;      // stage T: two K-block items per vehicle slot
+  DTL(0);
+  // The GNN kernel left this tile's inputs (st.dqp: per-tour means + features, st.dq: node statistics) in HBM: request
+  // them into L2 now, so that the A-tile loads of stage T and the query hand-over find them there
+  for (int e = tid; e < DT_M * 4 * 5; e += DT_THREADS) {        // (rollout, slot, 128-byte line 0..4 of the 532 bytes read)
+    const int r = e / 20, rem = e - r * 20, t = rem / 5, ln = rem - t * 5;
+    if (b0 + r < bs && t < K)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(st.dqp + ((size_t)(b0 + r) * 4 + t) * 256 + ln * 32));
+  }
+  for (int e = tid; e < DT_M * 16; e += DT_THREADS)
+    if (b0 + (e >> 4) < bs) asm volatile("prefetch.global.L2 [%0];" ::"l"(st.dq + (size_t)(b0 + (e >> 4)) * 512 + (e & 15) * 32));
+  const int n_t = 3 * K, n_items = n_t + DT_ITEMS;      // stage T: three K-block items per vehicle slot
   const uint8_t* wdec = reinterpret_cast<const uint8_t*>(a.w16) + (size_t)W16_DEC * 2;
-  auto issue_b = [&](int i) {          // one thread
+  auto issue_b = [&](int i) {          // one thread; the buffer's previous reader (item i - 2) must be complete
     uint32_t off, elems;
     dt_item_src(i, n_t, off, elems);
     const int buf = i & 1;
@@ -171,9 +189,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   if (tid == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(&bar_mma[0], 1);
+    mbar_init(&bar_mma[1], 1);
     mbar_fence_init();
     issue_b(0);
+    issue_b(1);
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -184,55 +204,54 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   const int q4 = warp & 3, cg = warp >> 2;            // TMEM lane quarter, column group of this warp
   const int r_t = q4 * 32 + lane;                     // accumulator row (= rollout of the tile) owned in TMEM accesses
   const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16);
-  const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), b_addr = smem_u32(sB);
+  const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
   const uint32_t idesc256 = umma_idesc(128, 256, Elem<T>::fmt), idesc64 = umma_idesc(128, 64, Elem<T>::fmt);
+  DTL(9);
 
-  // A tile from a row-major fp32 matrix in HBM: thread = (row tid / 4, 16-column group tid % 4).  Two halves: the loads
-  // of the NEXT item are issued before the wait for the current item's MMAs, the tile is written after it
-  auto load_global = [&](float (&v)[16], const float* src, size_t row_stride, int col0) {
-    const int r = tid >> 2, g = tid & 3;
-    if (b0 + r < bs) {
-      const float4* p = reinterpret_cast<const float4*>(src + (size_t)(b0 + r) * row_stride + col0 + g * 16);
+  // ---- the GEMM chain.  Items are numbered in program order; item i uses operand buffers i & 1 (A tile written by the
+  // threads, B tile streamed by the copy engine) and completion barrier bar_mma[i & 1].  Two items are in flight: while
+  // the tensor pipe works on item i the threads fill the A tile of item i + 1, so an item costs max(MMAs, tile fill)
+  // instead of their sum.  Rules: the A tile of item i is written after every thread has seen item i - 2 complete; the
+  // B tile of item i is requested after thread 0 has seen item i - 2 complete.
+  // A tile from a row-major fp32 matrix in HBM: 2048 float4 per tile, thread owns float4 (j * 512 + tid): a warp reads two
+  // whole 256-byte row segments per instruction
+  auto load_global = [&](float4 (&v)[4], const float* src, size_t row_stride, int col0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 x = p[i];
-        v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+    for (int j = 0; j < 4; ++j) {
+      const int r = j * 32 + (tid >> 4);
+      v[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (b0 + r < bs) v[j] = *reinterpret_cast<const float4*>(src + (size_t)(b0 + r) * row_stride + col0 + (tid & 15) * 4);
     }
   };
-  auto store_tile = [&](const float (&v)[16]) { write_a16<T>(sAhi, sAlo, tid >> 2, tid & 3, v); };
+  auto store_tile = [&](int i, const float4 (&v)[4]) {
+    uint8_t* hi = sA + (size_t)(i & 1) * 32768;
+    uint8_t* lo = hi + 16384;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t r = (uint32_t)(j * 32 + (tid >> 4)), c4 = (uint32_t)(tid & 15);      // columns 4 c4 .. 4 c4 + 3
+      const T2 h0 = Elem<T>::from2(v[j].x, v[j].y), h1 = Elem<T>::from2(v[j].z, v[j].w);
+      const float2 f0 = Elem<T>::to2(h0), f1 = Elem<T>::to2(h1);
+      const T2 l0 = Elem<T>::from2(v[j].x - f0.x, v[j].y - f0.y), l1 = Elem<T>::from2(v[j].z - f1.x, v[j].w - f1.y);
+      const uint32_t o = sw128_off(r, c4 >> 1) + (c4 & 1u) * 8u;
+      *reinterpret_cast<uint2*>(hi + o) = make_uint2(as_u32(h0), as_u32(h1));
+      *reinterpret_cast<uint2*>(lo + o) = make_uint2(as_u32(l0), as_u32(l1));
+    }
+  };
   // A tile from 64 accumulator columns in TMEM: warp = (lane quarter, 16-column group)
-  auto fill_from_tmem = [&](uint32_t col0) {
+  auto fill_from_tmem = [&](int i, uint32_t col0) {
     uint32_t raw[16];
     tmem_ld16_nowait(ta + col0 + (uint32_t)cg * 16u, raw);
     tmem_wait_ld();
     float v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-    write_a16<T>(sAhi, sAlo, r_t, cg, v);
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+    uint8_t* hi = sA + (size_t)(i & 1) * 32768;
+    write_a16<T>(hi, hi + 16384, r_t, cg, v);
   };
-  // accumulator columns [col0, col0 + 256) -> row-major fp32 rows in HBM (dst row stride in floats)
-  auto drain_to_global = [&](uint32_t col0, float* dst, size_t row_stride) {
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t raw[32];
-      tmem_ld32_nowait(ta + col0 + (uint32_t)(cg * 64 + c * 32), raw);
-      tmem_wait_ld();
-      if (b0 + r_t < bs) {
-        float4* o = reinterpret_cast<float4*>(dst + (size_t)(b0 + r_t) * row_stride + cg * 64 + c * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]),
-                             __uint_as_float(raw[4 * i + 3]));
-      }
-    }
-  };
-  // one item, first half: the A tile is filled; issue the next B load, wait for this one, 12 MMAs (4 K steps x hi*hi,
-  // lo*hi, hi*lo), commit.  Second half: every thread waits for the MMAs (A tile and accumulator free / valid).
-  auto issue_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first, bool prefetch = true) {
+  // block barrier, then thread 0 issues the MMAs of item i: nks K steps x (hi*hi, lo*hi, hi*lo) into accumulator columns
+  // d_col (and, stage T, a second time into d_col2 >= 0), commits, and requests the B tile of item i + 1
+  auto issue_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first, int nks = 4, int d_col2 = -1, bool first2 = false,
+                        bool prefetch = true) {
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -240,133 +259,207 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       tc_fence_after();
       mbar_wait(&full[i & 1], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
+      const uint32_t ah = a_addr + (uint32_t)(i & 1) * 32768u, al = ah + 16384u;
       const uint32_t bh = b_addr + (uint32_t)(i & 1) * 65536u, bl = bh + 32768u;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t dah = umma_desc_sw128(a_hi + ks * 32), dal = umma_desc_sw128(a_lo + ks * 32);
+#ifdef JAMPR_DT_NKS1
+      nks = 1;          // timing experiment: a quarter of the MMA work (results are wrong)
+#endif
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint64_t dah = umma_desc_sw128(ah + ks * 32), dal = umma_desc_sw128(al + ks * 32);
         const uint64_t dbh = umma_desc_sw128(bh + ks * 32), dbl = umma_desc_sw128(bl + ks * 32);
         umma_f16(tmem + d_col, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
         umma_f16(tmem + d_col, dal, dbh, idesc, 1u);
         umma_f16(tmem + d_col, dah, dbl, idesc, 1u);
+        if (d_col2 >= 0) {
+          umma_f16(tmem + (uint32_t)d_col2, dah, dbh, idesc, (first2 && ks == 0) ? 0u : 1u);
+          umma_f16(tmem + (uint32_t)d_col2, dal, dbh, idesc, 1u);
+          umma_f16(tmem + (uint32_t)d_col2, dah, dbl, idesc, 1u);
+        }
       }
-      umma_commit(bar_mma);
-      if (prefetch && i + 1 < n_items) issue_b(i + 1);     // off the critical path; its buffer was last read by item i - 1 (complete)
+      umma_commit(&bar_mma[i & 1]);
+      if (i >= 1 && prefetch && i + 1 < n_items) {
+        mbar_wait(&bar_mma[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));      // item i - 1 read the buffer of item i + 1
+        issue_b(i + 1);
+      }
     }
   };
   auto wait_item = [&](int i) {
-    mbar_wait(bar_mma, (uint32_t)(i & 1));
+    mbar_wait(&bar_mma[i & 1], (uint32_t)((i >> 1) & 1));
     tc_fence_after();
   };
-  auto run_item = [&](int i, uint32_t d_col, uint32_t idesc, bool first, bool prefetch = true) {
-    issue_item(i, d_col, idesc, first, prefetch);
-    wait_item(i);
+  // ---- accumulator rows -> HBM with whole-row-segment accesses.  tcgen05.ld hands a thread 32 columns of ITS row; stored
+  // directly that is 32 different 128-byte lines per warp instruction (the launch was bound by exactly that).  Each warp
+  // turns its 32 x 32 block through 4 KB of shared memory (16-byte chunks XOR-ed with the row: conflict-free both ways)
+  // and calls f(j, row of the tile, column, float4), j = 0..7, with 8 lanes covering 128 contiguous bytes of one row
+  // (row = 32 q4 + 4 j + lane / 8, column = col0 + 4 (lane % 8)).  The turn-table
+  // lives in the B buffer of the item that just completed (`buf`), which the copy engine refills only later.
+  auto coop_block = [&](int buf, const uint32_t (&vals)[32], int col0, auto&& f) {
+    uint8_t* tt = sB + (size_t)buf * 65536 + (size_t)warp * 4096;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<uint4*>(tt + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(vals[4 * c], vals[4 * c + 1], vals[4 * c + 2], vals[4 * c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rw = 4 * j + (lane >> 3), c = lane & 7;
+      const uint4 x = *reinterpret_cast<const uint4*>(tt + rw * 128 + ((c ^ (rw & 7)) << 4));
+      f(j, q4 * 32 + rw, col0 + 4 * c, make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)));
+    }
+    __syncwarp();
+  };
+  // accumulator columns [col0, col0 + 256) -> row-major fp32 rows in HBM (dst row stride in floats)
+  auto drain_to_global = [&](int buf, uint32_t col0, float* dst, size_t row_stride) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32_nowait(ta + col0 + (uint32_t)(cg * 64 + c * 32), raw);
+      tmem_wait_ld();
+      coop_block(buf, raw, cg * 64 + c * 32, [&](int, int row, int col, float4 x) {
+        if (b0 + row < bs) *reinterpret_cast<float4*>(dst + (size_t)(b0 + row) * row_stride + col) = x;
+      });
+    }
   };
 
-  // ================================================================ stage T: per-tour-mean half of the tour embeddings
-  // tour_encoder.py:202-213: tour_emb[t] = W_to [input_proj(features_t) | mean_h[t]] + b.  The mean half is a GEMM over
-  // the 128 rollouts of the tile per vehicle slot (A = the per-tour means the GNN kernel left in st.dqp[:, t, 0..127]);
-  // its raw result goes to st.dte, the feature half (folded 5 x 256 matrix) is added in the pass below.
+  // ================================================================ stage T: tour embeddings and the decoder query
+  // tour_encoder.py:202-213: tour_emb[t] = W_to [input_proj(features_t) | mean_h[t]] + b as one product over K = 192 per
+  // vehicle slot: A = [per-tour mean of h (128) | features (5), 1, 0 ..] from st.dqp[:, t, 0..132] left by the GNN kernel
+  // (the folded feature matrix and bias are K rows 0..5 of the third B tile).  Every item also accumulates into columns 256..511, which
+  // end up holding sum_t tour_emb[t]; the running maximum over the slots stays in registers (thread = row, 64 columns).
+  // policy.py:179-182: q = [mean_n(node_emb) + mean_t(tour_emb), max_n(node_emb) + max_t(tour_emb)]; st.dq arrives
+  // holding the node statistics and leaves holding q.
   {
-    float v[16];
+    float mx[64];
+    float4 v[4];
     load_global(v, st.dqp, 1024, 0);
 #pragma unroll 1
     for (int e = 0; e < n_t; ++e) {
-      const int t = e >> 1, kb = e & 1;
-      store_tile(v);
-      issue_item(e, 0u, idesc256, kb == 0);
-      if (e + 1 < n_t) load_global(v, st.dqp + (size_t)((e + 1) >> 1) * 256, 1024, ((e + 1) & 1) * 64);
-      wait_item(e);
-      if (kb == 1) {
-        drain_to_global(0u, st.dte + (size_t)t * 256, 1024);
-        tc_fence_before();
+      const int t = e / 3, kb = e - 3 * t;
+      if (e >= 2) wait_item(e - 2);
+      store_tile(e, v);
+      if (e == 0) DTL(10);
+      issue_item(e, 0u, idesc256, kb == 0, kb == 2 ? 1 : 4, 256, e == 0);
+      if (e == 0) DTL(11);
+      if (e + 1 < n_t) {
+        const int tn = (e + 1) / 3, kn = (e + 1) - 3 * tn;
+        load_global(v, st.dqp + (size_t)tn * 256, 1024, kn * 64);
+        if (kn == 2) {           // feature block [f0 .. f4, 1 (bias row), 0 ..]: the GNN kernel left the five features
+          const int c4 = tid & 15;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (c4 == 1) v[j] = make_float4(v[j].x, 1.0f, 0.0f, 0.0f);
+            else if (c4 > 1) v[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          }
+        }
+      }
+      if (kb == 2) {
+        wait_item(e);
+        if (e == 2) DTL(12);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld32_nowait(ta + (uint32_t)(cg * 64 + c * 32), raw);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx[c * 32 + j] = (t == 0) ? __uint_as_float(raw[j]) : fmaxf(mx[c * 32 + j], __uint_as_float(raw[j]));
+          coop_block(e & 1, raw, cg * 64 + c * 32, [&](int, int row, int col, float4 x) {
+            if (b0 + row < bs) *reinterpret_cast<float4*>(st.dte + ((size_t)(b0 + row) * 4 + t) * 256 + col) = x;
+          });
+        }
+        tc_fence_before();           // the next slot's first MMA overwrites these columns after the barrier in issue_item
+        if (e == 2) DTL(13);
       }
     }
-  }
-  __threadfence_block();
-  __syncthreads();
-  // ---- per rollout (one warp, lane = 8 columns): tour embeddings and the decoder query (policy.py:179-182)
-  // q = [mean_n(node_emb) + mean_t(tour_emb), max_n(node_emb) + max_t(tour_emb)]; st.dq arrives holding the node statistics
-  {
-  const int c0 = lane * 8;
-  float bias[8], wt[5][8];                 // folded tour-feature branch for this lane's columns: the same for every rollout
-  {
-    const float4* pb = reinterpret_cast<const float4*>(a.w + OFF_TOF_B + c0);
-    const float4 x = __ldg(pb), y = __ldg(pb + 1);
-    bias[0] = x.x; bias[1] = x.y; bias[2] = x.z; bias[3] = x.w; bias[4] = y.x; bias[5] = y.y; bias[6] = y.z; bias[7] = y.w;
+    DTL(14);
+    // q: mean part from the summed accumulators, max part from the registers.  The node statistics of the rows / columns
+    // this lane hands over are requested first, all at once (a read-modify-write per element would be a chain of
+    // dependent round trips)
+    const int lbuf = (n_t - 1) & 1;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const float4* pw = reinterpret_cast<const float4*>(a.w + OFF_TOF_WT + i * 256 + c0);
-      const float4 u = __ldg(pw), z = __ldg(pw + 1);
-      wt[i][0] = u.x; wt[i][1] = u.y; wt[i][2] = u.z; wt[i][3] = u.w; wt[i][4] = z.x; wt[i][5] = z.y; wt[i][6] = z.z; wt[i][7] = z.w;
-    }
-  }
-#pragma unroll 1
-  for (int rr = warp; rr < DT_M; rr += DT_WARPS) {
-    const int b = b0 + rr;
-    if (b >= bs) break;
-    if (jampr_rollout_idle(st, b, K)) continue;
-    float sum[8], mx[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; mx[j] = -INFINITY; }
-    for (int t = 0; t < K; ++t) {
-      float* pt = st.dte + ((size_t)b * 4 + t) * 256 + c0;
-      const float* pf = st.dqp + ((size_t)b * 4 + t) * 256 + 128;
-      const float4 x = *reinterpret_cast<const float4*>(pt), y = *reinterpret_cast<const float4*>(pt + 4);
-      const float gm[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-      float f[5];
-#pragma unroll
-      for (int i = 0; i < 5; ++i) f[i] = pf[i];
-      float te[8];
+    for (int c = 0; c < 2; ++c) {            // max part first: it releases the registers of the running maximum
+      float4 nx[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float v = bias[j];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) v = fmaf(f[i], wt[i][j], v);
-        v += gm[j];
-        te[j] = v;
-        sum[j] += v;
-        mx[j] = fmaxf(mx[j], v);
+        const int row = q4 * 32 + 4 * j + (lane >> 3), col = cg * 64 + c * 32 + 4 * (lane & 7);
+        nx[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (b0 + row < bs) nx[j] = *reinterpret_cast<const float4*>(st.dq + (size_t)(b0 + row) * 512 + 256 + col);
       }
-      *reinterpret_cast<float4*>(pt) = make_float4(te[0], te[1], te[2], te[3]);
-      *reinterpret_cast<float4*>(pt + 4) = make_float4(te[4], te[5], te[6], te[7]);
+      uint32_t raw[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(mx[c * 32 + j]);
+      coop_block(lbuf, raw, cg * 64 + c * 32, [&](int j, int row, int col, float4 x) {
+        if (b0 + row < bs)
+          *reinterpret_cast<float4*>(st.dq + (size_t)(b0 + row) * 512 + 256 + col) =
+              make_float4(nx[j].x + x.x, nx[j].y + x.y, nx[j].z + x.z, nx[j].w + x.w);
+      });
     }
-    float* pq = st.dq + (size_t)b * 512 + c0;
-    const float4 m0 = *reinterpret_cast<const float4*>(pq), m1 = *reinterpret_cast<const float4*>(pq + 4);
-    const float4 x0 = *reinterpret_cast<const float4*>(pq + 256), x1 = *reinterpret_cast<const float4*>(pq + 260);
-    // same operation order as the fused kernel: nmean + sum / K, nmax + max
-    *reinterpret_cast<float4*>(pq) = make_float4(m0.x + sum[0] / (float)K, m0.y + sum[1] / (float)K, m0.z + sum[2] / (float)K, m0.w + sum[3] / (float)K);
-    *reinterpret_cast<float4*>(pq + 4) = make_float4(m1.x + sum[4] / (float)K, m1.y + sum[5] / (float)K, m1.z + sum[6] / (float)K, m1.w + sum[7] / (float)K);
-    *reinterpret_cast<float4*>(pq + 256) = make_float4(x0.x + mx[0], x0.y + mx[1], x0.z + mx[2], x0.w + mx[3]);
-    *reinterpret_cast<float4*>(pq + 260) = make_float4(x1.x + mx[4], x1.y + mx[5], x1.z + mx[6], x1.w + mx[7]);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float4 nm[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = q4 * 32 + 4 * j + (lane >> 3), col = cg * 64 + c * 32 + 4 * (lane & 7);
+        nm[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (b0 + row < bs) nm[j] = *reinterpret_cast<const float4*>(st.dq + (size_t)(b0 + row) * 512 + col);
+      }
+      uint32_t raw[32];
+      tmem_ld32_nowait(ta + 256u + (uint32_t)(cg * 64 + c * 32), raw);
+      tmem_wait_ld();
+      coop_block(lbuf, raw, cg * 64 + c * 32, [&](int j, int row, int col, float4 x) {
+        // same operation order as the fused kernel: nmean + sum / K
+        if (b0 + row < bs)
+          *reinterpret_cast<float4*>(st.dq + (size_t)(b0 + row) * 512 + col) =
+              make_float4(nm[j].x + x.x / (float)K, nm[j].y + x.y / (float)K, nm[j].z + x.z / (float)K, nm[j].w + x.w / (float)K);
+      });
+    }
+    tc_fence_before();
   }
-  }
+  DTL(15);
   __threadfence_block();
-  __syncthreads();
+  __syncthreads();               // st.dq / st.dte rows of this tile are visible to every warp of the CTA
+  DTL(1);
+  DTL(2);
 
   // ================================================================ stage A: ctxt (TMEM columns 0..255)
+  // (A data requested two items ahead: a load has one whole item to arrive)
   {
-    float v[16];
-    load_global(v, st.dq, 512, 0);
+    float4 va[4], vb[4];
+    load_global(va, st.dq, 512, 0);
+    load_global(vb, st.dq, 512, 64);
 #pragma unroll 1
-    for (int kb = 0; kb < 8; ++kb) {
-      store_tile(v);
-      issue_item(n_t + kb, 0u, idesc256, kb == 0);
-      if (kb + 1 < 8) load_global(v, st.dq, 512, (kb + 1) * 64);
-      wait_item(n_t + kb);
+    for (int kb = 0; kb < 8; kb += 2) {
+      const int i = n_t + kb;
+      wait_item(i - 2);
+      store_tile(i, va);
+      issue_item(i, 0u, idesc256, kb == 0);
+      if (kb + 2 < 8) load_global(va, st.dq, 512, (kb + 2) * 64);
+      wait_item(i - 1);
+      store_tile(i + 1, vb);
+      issue_item(i + 1, 0u, idesc256, false);
+      if (kb + 3 < 8) load_global(vb, st.dq, 512, (kb + 3) * 64);
     }
   }
+  DTL(3);
   // ================================================================ stage B: qp_h (TMEM columns 256..511) -> st.dqp
+  {
+    const int i0 = n_t + 8;
+    wait_item(i0 - 1);           // ctxt complete (and with it item i0 - 2)
+    fill_from_tmem(i0, 0u);
+    issue_item(i0, 256u, idesc256, true);
 #pragma unroll 1
-  for (int h = 0; h < 4; ++h) {
-    fill_from_tmem((uint32_t)h * 64u);
-    run_item(n_t + 8 + h, 256u, idesc256, true, h < 3);      // no B tile in flight during phase C: it overlays the buffers
-    drain_to_global(256u, st.dqp + (size_t)h * 256, 1024);
-    tc_fence_before();           // the next item's MMAs overwrite these columns after the block barrier in run_item
+    for (int h = 0; h < 4; ++h) {
+      const int i = i0 + h;
+      if (h < 3) fill_from_tmem(i + 1, (uint32_t)(h + 1) * 64u);      // A buffer of item i - 1: complete since the last drain
+      wait_item(i);
+      drain_to_global(i & 1, 256u, st.dqp + (size_t)h * 256, 1024);
+      tc_fence_before();           // the next item's MMAs overwrite these columns after the block barrier in issue_item
+      if (h < 3) issue_item(i + 1, 256u, idesc256, true, 4, -1, false, h < 2);   // no B tile in flight during phase C
+    }
   }
   __threadfence_block();
   __syncthreads();               // st.dqp rows of this tile are visible to every warp of the CTA (same SM, L1 coherent
                                  // for data written by the CTA itself; reads below use plain loads)
 
+  DTL(4);
   // ================================================================ phase C: glimpse per rollout (one warp each)
   const T* ne16 = reinterpret_cast<const T*>(st.ne16);
   const int g8 = lane >> 2, t4 = lane & 3;            // mma fragment coordinates
@@ -378,24 +471,37 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   // feasible actions of rollout b in ascending order -> s_list (action | slot << 10), s_nb; returns their number
   auto build_list = [&](int b, bool init_logits) {
     int cnt = 0;
-    for (int e0 = 0; e0 < A; e0 += 32) {
-      const int e = e0 + lane;
-      bool ok = false;
-      if (e < A) {
-        s_nb[e] = st.nbh[(size_t)b * A + e];
-        ok = st.mask[(size_t)b * A + e] == 0;
-        if (init_logits) s_logit[e] = -INFINITY;
+    for (int e00 = 0; e00 < A; e00 += 128) {        // 128 actions per round trip
+      int nb[4], mk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = e00 + 32 * j + lane;
+        nb[j] = 0;
+        mk[j] = 1;
+        if (e < A) {
+          nb[j] = st.nbh[(size_t)b * A + e];
+          mk[j] = st.mask[(size_t)b * A + e];
+        }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (ok) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (int16_t)(e | ((e / k) << 10));      // action | slot << 10
-      cnt += __popc(m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = e00 + 32 * j + lane;
+        if (e < A) {
+          s_nb[e] = (int16_t)nb[j];
+          if (init_logits) s_logit[e] = -INFINITY;
+        }
+        const bool ok = mk[j] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (int16_t)(e | ((e / k) << 10));      // action | slot << 10
+        cnt += __popc(m);
+      }
     }
     __syncwarp();
     return cnt;
   };
   // rows of the feasible actions i0 .. i0+15 -> sR (rows past the end are zero-filled: they enter the glimpse MMA with
   // weight 0 and must be finite)
-  auto stage_rows = [&](const uint8_t* rows_b, int i0, int cnt) {
+  auto stage_issue = [&](const uint8_t* rows_b, int i0, int cnt) {
     int goff = 0;
     if (lane < DT_RROWS) goff = (int)s_nb[s_list[min(i0 + lane, cnt - 1)] & 1023] * 512;
 #pragma unroll
@@ -406,25 +512,35 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
                    "l"(rows_b + off), "r"(nbytes)
                    : "memory");
     }
+  };
+  auto stage_wait = [&]() {
     cp_async_wait_all();
     __syncwarp();
   };
   // S[v][a] = sum_c Q[v][c] R[a][c] for the 16 staged rows: this lane ends up with the full dot products (hi + lo) of
   // query vector g8 & 3 for the chunk positions 2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4
+  // (mma.sync has a dependent-issue latency of ~260 cycles on this part, tools/ubench/hmma_rate.cu: the 16 K steps run as
+  // two independent accumulation chains per n-tile, summed at the end; four chains spill next to the glimpse accumulators)
   auto chunk_scores = [&](float (&sc)[4]) {
-    float acc0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 4
+    float acc0[2][4], acc1[2][4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc0[p][j] = 0.0f; acc1[p][j] = 0.0f; }
+#pragma unroll
     for (int ks = 0; ks < 16; ++ks) {
       uint32_t b00, b01, b10, b11, a0, a2;
       ldsm_x4(r_lm + (uint32_t)ks * 32u, b00, b01, b10, b11);
       ldsm_x2(q_lm + (uint32_t)ks * 32u, a0, a2);
-      mma16816<T>(acc0, a0, 0u, a2, 0u, b00, b01);
-      mma16816<T>(acc1, a0, 0u, a2, 0u, b10, b11);
+      mma16816<T>(acc0[ks & 1], a0, 0u, a2, 0u, b00, b01);
+      mma16816<T>(acc1[ks & 1], a0, 0u, a2, 0u, b10, b11);
     }
-    sc[0] = acc0[0] + __shfl_xor_sync(0xffffffffu, acc0[0], 16);
-    sc[1] = acc0[1] + __shfl_xor_sync(0xffffffffu, acc0[1], 16);
-    sc[2] = acc1[0] + __shfl_xor_sync(0xffffffffu, acc1[0], 16);
-    sc[3] = acc1[1] + __shfl_xor_sync(0xffffffffu, acc1[1], 16);
+    const float s0 = acc0[0][0] + acc0[1][0], s1 = acc0[0][1] + acc0[1][1];
+    const float s2 = acc1[0][0] + acc1[1][0], s3 = acc1[0][1] + acc1[1][1];
+    sc[0] = s0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+    sc[1] = s1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+    sc[2] = s2 + __shfl_xor_sync(0xffffffffu, s2, 16);
+    sc[3] = s3 + __shfl_xor_sync(0xffffffffu, s3, 16);
   };
   // fp32 vector (this lane's 8 columns) -> query rows `row` (hi) and 4 + `row` (lo)
   auto put_query = [&](int row, const float2 (&v)[4]) {
@@ -444,8 +560,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     const int b = b0 + rr;
     if (b >= bs) break;
     if (jampr_rollout_idle(st, b, K)) continue;
-    const int cnt = build_list(b, false);
-    // per-head glimpse query: lane owns columns 8 lane .. 8 lane + 7
+    // everything this rollout needs besides the rows is requested in one round trip: per-head glimpse queries and tour
+    // embeddings (lane owns columns 8 lane .. 8 lane + 7), then the action list
     float2 qv[4][4];
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
@@ -454,21 +570,37 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       qv[h][0] = make_float2(x.x, x.y); qv[h][1] = make_float2(x.z, x.w);
       qv[h][2] = make_float2(y.x, y.y); qv[h][3] = make_float2(y.z, y.w);
     }
-    for (int t = 0; t < K; ++t) {
-      const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
-      const float4 x = p[0], y = p[1];
-      const float2 v0 = make_float2(x.x, x.y), v1 = make_float2(x.z, x.w), v2 = make_float2(y.x, y.y), v3 = make_float2(y.z, y.w);
-      float dd[4];
+    float4 tex[4], tey[4];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        float2 e = __ffma2_rn(v0, qv[h][0], make_float2(0.0f, 0.0f));
-        e = __ffma2_rn(v1, qv[h][1], e);
-        e = __ffma2_rn(v2, qv[h][2], e);
-        e = __ffma2_rn(v3, qv[h][3], e);
-        dd[h] = e.x + e.y;
+    for (int t = 0; t < 4; ++t) {
+      tex[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      tey[t] = tex[t];
+      if (t < K) {
+        const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
+        tex[t] = p[0];
+        tey[t] = p[1];
       }
-      const float z = warp_sum4(dd[0], dd[1], dd[2], dd[3], lane);
-      if ((lane & 7) == 0) s_qt[(((lane >> 4) << 1) | ((lane >> 3) & 1)) * 4 + t] = z;
+    }
+    const int cnt = build_list(b, false);
+    const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(ne16 + (size_t)b * N * 256) + lane * 16;
+    stage_issue(rows_b, 0, cnt);                 // first chunk in flight during the query preparation
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (t < K) {
+        const float2 v0 = make_float2(tex[t].x, tex[t].y), v1 = make_float2(tex[t].z, tex[t].w);
+        const float2 v2 = make_float2(tey[t].x, tey[t].y), v3 = make_float2(tey[t].z, tey[t].w);
+        float dd[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float2 e = __ffma2_rn(v0, qv[h][0], make_float2(0.0f, 0.0f));
+          e = __ffma2_rn(v1, qv[h][1], e);
+          e = __ffma2_rn(v2, qv[h][2], e);
+          e = __ffma2_rn(v3, qv[h][3], e);
+          dd[h] = e.x + e.y;
+        }
+        const float z = warp_sum4(dd[0], dd[1], dd[2], dd[3], lane);
+        if ((lane & 7) == 0) s_qt[(((lane >> 4) << 1) | ((lane >> 3) & 1)) * 4 + t] = z;
+      }
     }
 #pragma unroll
     for (int h = 0; h < 4; ++h) put_query(h, qv[h]);
@@ -478,7 +610,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     float qt_r[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) qt_r[q] = (q < K) ? s_qt[hh * 4 + q] : 0.0f;
-    const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(ne16 + (size_t)b * N * 256) + lane * 16;
     // online softmax over the chunks: running maximum m_run, this lane's partial denominator l_part and per-slot
     // partial weight sums ps[] (all relative to m_run), glimpse accumulators G[c][v] (v < 4: hi of p, v >= 4: lo of p)
     float m_run = -INFINITY, l_part = 0.0f, ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -487,7 +618,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     for (int i = 0; i < 16; ++i) { G[i][0] = 0.0f; G[i][1] = 0.0f; G[i][2] = 0.0f; G[i][3] = 0.0f; }
 #pragma unroll 1
     for (int i0 = 0; i0 < cnt; i0 += DT_RROWS) {
-      stage_rows(rows_b, i0, cnt);
+      if (i0 > 0) stage_issue(rows_b, i0, cnt);
+      stage_wait();
       float sc[4];
       chunk_scores(sc);
       const uint32_t lwA = *reinterpret_cast<const uint32_t*>(s_list + i0 + 2 * t4);
@@ -553,7 +685,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       ps[q] *= inv;
     }
     // accumulators -> [8][256] fp32 in the (dead) row buffer, then per lane 8 columns x 4 heads:
-    // gbar_h = (hi + lo) / denominator + sum_t P_h[t] tour_emb[t]
+    // gbar_h = (hi + lo) / denominator + sum_t P_h[t] tour_emb[t]   (tour embeddings re-requested first: L1 / L2 hits
+    // whose latency overlaps the hand-over)
     {
       float* sG = reinterpret_cast<float*>(sR);
 #pragma unroll
@@ -562,6 +695,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
         sG[(2 * t4 + 1) * DT_GSTRIDE + 16 * i + g8] = G[i][1];
         sG[(2 * t4) * DT_GSTRIDE + 16 * i + g8 + 8] = G[i][2];
         sG[(2 * t4 + 1) * DT_GSTRIDE + 16 * i + g8 + 8] = G[i][3];
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t < K) {
+          const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
+          tex[t] = p[0];
+          tey[t] = p[1];
+        }
       }
       __syncwarp();
       float2 gb[4][4];
@@ -577,18 +718,19 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
         gb[h][2] = make_float2((y.x + v.x) * ih, (y.y + v.y) * ih);
         gb[h][3] = make_float2((y.z + v.z) * ih, (y.w + v.w) * ih);
       }
-      for (int t = 0; t < K; ++t) {
-        const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
-        const float4 x = p[0], y = p[1];
-        const float2 t0 = make_float2(x.x, x.y), t1 = make_float2(x.z, x.w), t2 = make_float2(y.x, y.y), t3 = make_float2(y.z, y.w);
-        const float pst = (t == 0) ? ps[0] : (t == 1) ? ps[1] : (t == 2) ? ps[2] : ps[3];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float2 p2 = f2(__shfl_sync(0xffffffffu, pst, 4 * h));
-          gb[h][0] = __ffma2_rn(p2, t0, gb[h][0]);
-          gb[h][1] = __ffma2_rn(p2, t1, gb[h][1]);
-          gb[h][2] = __ffma2_rn(p2, t2, gb[h][2]);
-          gb[h][3] = __ffma2_rn(p2, t3, gb[h][3]);
+      for (int t = 0; t < 4; ++t) {
+        if (t < K) {
+          const float2 t0 = make_float2(tex[t].x, tex[t].y), t1 = make_float2(tex[t].z, tex[t].w);
+          const float2 t2 = make_float2(tey[t].x, tey[t].y), t3 = make_float2(tey[t].z, tey[t].w);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float2 p2 = f2(__shfl_sync(0xffffffffu, ps[t], 4 * h));
+            gb[h][0] = __ffma2_rn(p2, t0, gb[h][0]);
+            gb[h][1] = __ffma2_rn(p2, t1, gb[h][1]);
+            gb[h][2] = __ffma2_rn(p2, t2, gb[h][2]);
+            gb[h][3] = __ffma2_rn(p2, t3, gb[h][3]);
+          }
         }
       }
 #pragma unroll
@@ -604,27 +746,40 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   __threadfence_block();
   __syncthreads();
   if (tid == 0) issue_b(n_t + 12);
+  DTL(5);
 
   // ================================================================ stage D: g (TMEM columns 0..255, 64 per head)
   {
-    float v[16];
-    load_global(v, st.dgbar, 1024, 0);
+    float4 va[4], vb[4];
+    load_global(va, st.dgbar, 1024, 0);
+    load_global(vb, st.dgbar, 1024, 64);
 #pragma unroll 1
-    for (int e = 0; e < 16; ++e) {
-      const int h = e >> 2, kb = e & 3;
-      store_tile(v);
-      issue_item(n_t + 12 + e, (uint32_t)h * 64u, idesc64, kb == 0);
-      if (e + 1 < 16) load_global(v, st.dgbar + (size_t)((e + 1) >> 2) * 256, 1024, ((e + 1) & 3) * 64);
-      wait_item(n_t + 12 + e);
+    for (int e = 0; e < 16; e += 2) {
+      const int h = e >> 2, kb = e & 3, i = n_t + 12 + e;      // items e, e + 1 belong to the same head
+      wait_item(i - 2);
+      store_tile(i, va);
+      issue_item(i, (uint32_t)h * 64u, idesc64, kb == 0);
+      if (e + 2 < 16) load_global(va, st.dgbar + (size_t)((e + 2) >> 2) * 256, 1024, ((e + 2) & 3) * 64);
+      wait_item(i - 1);
+      store_tile(i + 1, vb);
+      issue_item(i + 1, (uint32_t)h * 64u, idesc64, false);
+      if (e + 3 < 16) load_global(vb, st.dgbar + (size_t)((e + 3) >> 2) * 256, 1024, ((e + 3) & 3) * 64);
     }
   }
+  DTL(6);
   // ================================================================ stage E: lp (TMEM columns 256..511) -> st.dlp
+  {
+    const int i0 = n_t + 28;
+    wait_item(i0 - 1);           // g complete
 #pragma unroll 1
-  for (int kb = 0; kb < 4; ++kb) {
-    fill_from_tmem((uint32_t)kb * 64u);
-    run_item(n_t + 28 + kb, 256u, idesc256, kb == 0);
+    for (int kb = 0; kb < 4; ++kb) {
+      if (kb >= 2) wait_item(i0 + kb - 2);
+      fill_from_tmem(i0 + kb, (uint32_t)kb * 64u);
+      issue_item(i0 + kb, 256u, idesc256, kb == 0);
+    }
+    wait_item(i0 + 3);
+    drain_to_global((i0 + 3) & 1, 256u, st.dlp, 256);
   }
-  drain_to_global(256u, st.dlp, 256);
   tc_fence_before();
   __threadfence_block();
   __syncthreads();
@@ -632,6 +787,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+  DTL(7);
 
   // ================================================================ phase F: logits + selection per rollout
 #pragma unroll 1
@@ -647,34 +803,46 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       }
       continue;
     }
-    const int cnt = build_list(b, true);
+    // logit vector and tour embeddings requested together with the action list (one round trip)
     float2 lv[4];
     {
       const float4* p = reinterpret_cast<const float4*>(st.dlp + (size_t)b * 256 + lane * 8);
       const float4 x = p[0], y = p[1];
       lv[0] = make_float2(x.x, x.y); lv[1] = make_float2(x.z, x.w); lv[2] = make_float2(y.x, y.y); lv[3] = make_float2(y.z, y.w);
     }
-    float lt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    for (int t = 0; t < K; ++t) {
-      const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
-      const float4 x = p[0], y = p[1];
-      float2 e = __ffma2_rn(make_float2(x.x, x.y), lv[0], make_float2(0.0f, 0.0f));
-      e = __ffma2_rn(make_float2(x.z, x.w), lv[1], e);
-      e = __ffma2_rn(make_float2(y.x, y.y), lv[2], e);
-      e = __ffma2_rn(make_float2(y.z, y.w), lv[3], e);
-      const float z = warp_sum(e.x + e.y);
+    float4 tex[4], tey[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j == t) lt[j] = z;
+    for (int t = 0; t < 4; ++t) {
+      tex[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      tey[t] = tex[t];
+      if (t < K) {
+        const float4* p = reinterpret_cast<const float4*>(st.dte + ((size_t)b * 4 + t) * 256 + lane * 8);
+        tex[t] = p[0];
+        tey[t] = p[1];
+      }
+    }
+    const int cnt = build_list(b, true);
+    const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(ne16 + (size_t)b * N * 256) + lane * 16;
+    stage_issue(rows_b, 0, cnt);
+    float lt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (t < K) {
+        float2 e = __ffma2_rn(make_float2(tex[t].x, tex[t].y), lv[0], make_float2(0.0f, 0.0f));
+        e = __ffma2_rn(make_float2(tex[t].z, tex[t].w), lv[1], e);
+        e = __ffma2_rn(make_float2(tey[t].x, tey[t].y), lv[2], e);
+        e = __ffma2_rn(make_float2(tey[t].z, tey[t].w), lv[3], e);
+        lt[t] = warp_sum(e.x + e.y);
+      }
     }
     // logit vector as query row 0 (hi) / 4 (lo); the other query rows keep finite leftovers of phase C or zeros, and
     // rows of the score MMA are independent
     put_query(0, lv);
     __syncwarp();
-    const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(ne16 + (size_t)b * N * 256) + lane * 16;
 #pragma unroll 1
     for (int i0 = 0; i0 < cnt; i0 += DT_RROWS) {
-      stage_rows(rows_b, i0, cnt);
+      if (i0 > 0) stage_issue(rows_b, i0, cnt);
+      stage_wait();
       float sc[4];
       chunk_scores(sc);
       if (g8 == 0) {          // raw dot products; the clip follows, vectorised
@@ -758,7 +926,16 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     }
     __syncwarp();
   }
+  DTL(8);
 }
+
+#ifdef JAMPR_TIMELINE
+extern "C" __attribute__((visibility("default"))) int jampr_debug_dtimeline(uint32_t* host_out) {
+  CUDA_RET(cudaDeviceSynchronize());
+  CUDA_RET(cudaMemcpyFromSymbol(host_out, g_dtimeline, sizeof(g_dtimeline)));
+  return 0;
+}
+#endif
 
 static size_t dt_smem_bytes(const jampr_dims_t* d) { return 1024 + (size_t)dt_region_bytes(d->n_slots * d->k_nbh) + 64; }
 

@@ -17,14 +17,16 @@ using namespace tc;
 // split-decoder GEMM operands (decoder_tc.cu), B tiles [rows][64 K] in the 128-byte swizzle, a hi part followed by a lo
 // part (w = hi + lo, both 16-bit): ctxt_proj (256 x 512) as 8 K-block tiles; per head B[c][d] = set_proj[64h + d][c]
 // (256 x 64); per head 4 K-block tiles of set_proj[256 + 64h .. +64] (64 x 256); M1 = W_lk^T W_out (256 x 256) as 4 tiles;
-// tour_encoder.output_proj[:, 128:] (256 x 128, the per-tour-mean half) as 2 tiles
+// tour_encoder.output_proj[:, 128:] (256 x 128, the per-tour-mean half) as 2 tiles + the folded feature half as a third
 #define WD_TILE 16384                                   // elements of a [256 rows][64 K] tile (32 KB)
 #define WD_C 0
 #define WD_GK (WD_C + 8 * WD_TILE)
 #define WD_GV (WD_GK + 4 * WD_TILE)
 #define WD_M1 (WD_GV + 4 * WD_TILE)
-#define WD_TO (WD_M1 + 4 * WD_TILE)                     // tour output_proj, per-tour-mean half (256 x 128): 2 K-block tiles
-#define WD_PART (WD_TO + 2 * WD_TILE)                   // elements of one part (hi or lo)
+#define WD_TO (WD_M1 + 4 * WD_TILE)                     // tour output_proj: per-tour-mean half (256 x 128) as 2 K-block tiles, then
+                                                        // one tile whose K rows 0..4 are the folded tour-feature matrix
+                                                        // (OFF_TOF_WT) and K row 5 the folded bias (OFF_TOF_B), rest 0
+#define WD_PART (WD_TO + 3 * WD_TILE)                   // elements of one part (hi or lo)
 #define W16_DEC (W16_NE + 20 * W16_STAGE)
 #define W16_END (W16_DEC + 2 * WD_PART)
 

@@ -139,7 +139,13 @@ def pack_tc(sd: Dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16) ->
     mats += [sp[64 * h:64 * h + 64, :].t().contiguous() for h in range(4)]                 # (256, 64) per head: qp_h = B ctxt_h
     mats += [sp[256 + 64 * h:256 + 64 * h + 64, :].contiguous() for h in range(4)]         # (64, 256) per head: 4 tiles each
     mats += [m1]                                                                           # (256, 256): 4 tiles
-    mats += [sd["tour_encoder.output_proj.weight"][:, 128:].contiguous()]                  # (256, 128): 2 tiles, tour_emb
+    # tour_emb[t] = W_to [input_proj(features_t) | mean_h[t]] + b as ONE product over K = 192: the per-tour-mean half
+    # (128), then the folded feature half: 5 feature columns, the folded bias (multiplied by a constant-1 column), zeros
+    wto64 = sd["tour_encoder.output_proj.weight"].double()
+    feat = torch.zeros(256, 64, dtype=torch.float64)
+    feat[:, :5] = wto64[:, :128] @ sd["tour_encoder.input_proj.weight"].double()
+    feat[:, 5] = wto64[:, :128] @ sd["tour_encoder.input_proj.bias"].double() + sd["tour_encoder.output_proj.bias"].double()
+    mats += [torch.cat((sd["tour_encoder.output_proj.weight"][:, 128:], feat.float()), 1).contiguous()]   # (256, 192): 3 tiles
     hi = [m.to(dtype) for m in mats]
     lo = [(m - h_.float()).to(dtype) for m, h_ in zip(mats, hi)]
     for part in (hi, lo):
