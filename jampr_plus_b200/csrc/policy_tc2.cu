@@ -136,7 +136,13 @@ __device__ __forceinline__ void layer_epilogue2(uint32_t tmem, uint8_t* sA, uint
   }
   tmem_wait_st();
   s_red[ch * 128 + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
-  __syncthreads();
+  // the two halves of a row live in warps q and q + 4: only that pair has to meet (named barrier 1 + q, 64 threads)
+  switch (q) {            // literal ids: the kernel reserves five barriers, not sixteen
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
   const float2 v0 = s_red[r], v1 = s_red[128 + r];
   const float mean = (v0.x + v1.x) * (1.0f / 128.0f);
   const float var = fmaxf(fmaf(-mean, mean, (v0.y + v1.y) * (1.0f / 128.0f)), 0.0f);
@@ -671,9 +677,6 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
           mma_kblock(tmem, a_addr + 3 * ts, w_addr + 16384, idesc, false);
         }
         umma_commit(bar_root);
-        mbar_wait(bar_root, ph);                     // both stages free again: stream the second pair
-        load_w2<T>(sW, 0, a.w16, l * 4 + (proj ? 2 : 0), full);
-        load_w2<T>(sW, 1, a.w16, l * 4 + (proj ? 3 : 1), full);
       }
       if (!proj) {
         if (tid >= 32 && tid < 128)
@@ -683,6 +686,13 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
         else if (l < 2) agg_tour_tc2<T>(sA, ts, s_lf, ef_saddr, n_ef4, N);
         else agg_tour_tc2<T>(sA, ts, s_lr, er_saddr, n_er4, N);
         fence_proxy_async();
+      }
+      if (tid == 0) {
+        // warp 0's share of the aggregation ran while the lin_root MMAs executed; both stages are free once they are
+        // complete: stream the second pair
+        mbar_wait(bar_root, ph);
+        load_w2<T>(sW, 0, a.w16, l * 4 + (proj ? 2 : 0), full);
+        load_w2<T>(sW, 1, a.w16, l * 4 + (proj ? 3 : 1), full);
       }
       __syncthreads();
       TL(3 + 3 * l);
