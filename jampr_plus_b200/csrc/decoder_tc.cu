@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch);          // full[0], full[1], mma[0], mma[1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(scratch + 32);
   int* s_any = reinterpret_cast<int*>(scratch + 48);
+  int* s_next = reinterpret_cast<int*>(scratch + 52);            // [2]: next unclaimed rollout of the tile in phases C, F
   // per-warp region of the per-rollout phases (over the operand tiles)
   uint8_t* wbase = base + (size_t)warp * dt_warp_bytes(A);
   uint8_t* sR = wbase;                                                        // staged rows | glimpse hand-over
@@ -147,7 +148,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   uint64_t* bar_mma = bars + 2;            // [2]
 
   // ---- does any rollout of this tile need a decision?  (late in the episode whole tiles are idle)
-  if (tid == 0) *s_any = 0;
+  if (tid == 0) {
+    *s_any = 0;
+    s_next[0] = 0;
+    s_next[1] = 0;
+  }
   __syncthreads();
   {
     bool need = false;
@@ -167,15 +172,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   }
 
   DTL(0);
-  // The GNN kernel left this tile's inputs (st.dqp: per-tour means + features, st.dq: node statistics) in HBM: request
-  // them into L2 now, so that the A-tile loads of stage T and the query hand-over find them there
+  // The GNN kernel left this tile's per-tour means and features (st.dqp) in HBM: request them into L2 now, so that the
+  // A-tile loads of stage T find them there
   for (int e = tid; e < DT_M * 4 * 5; e += DT_THREADS) {        // (rollout, slot, 128-byte line 0..4 of the 532 bytes read)
     const int r = e / 20, rem = e - r * 20, t = rem / 5, ln = rem - t * 5;
     if (b0 + r < bs && t < K)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(st.dqp + ((size_t)(b0 + r) * 4 + t) * 256 + ln * 32));
   }
-  for (int e = tid; e < DT_M * 16; e += DT_THREADS)
-    if (b0 + (e >> 4) < bs) asm volatile("prefetch.global.L2 [%0];" ::"l"(st.dq + (size_t)(b0 + (e >> 4)) * 512 + (e & 15) * 32));
   const int n_t = 3 * K, n_items = n_t + DT_ITEMS;      // stage T: three K-block items per vehicle slot
   const uint8_t* wdec = reinterpret_cast<const uint8_t*>(a.w16) + (size_t)W16_DEC * 2;
   auto issue_b = [&](int i) {          // one thread; the buffer's previous reader (item i - 2) must be complete
@@ -325,8 +328,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   // vehicle slot: A = [per-tour mean of h (128) | features (5), 1, 0 ..] from st.dqp[:, t, 0..132] left by the GNN kernel
   // (the folded feature matrix and bias are K rows 0..5 of the third B tile).  Every item also accumulates into columns 256..511, which
   // end up holding sum_t tour_emb[t]; the running maximum over the slots stays in registers (thread = row, 64 columns).
-  // policy.py:179-182: q = [mean_n(node_emb) + mean_t(tour_emb), max_n(node_emb) + max_t(tour_emb)]; st.dq arrives
-  // holding the node statistics and leaves holding q.
+  // Sum and maximum go to stage A through two scratch rows per rollout.
   {
     float mx[64];
     float4 v[4];
@@ -370,72 +372,72 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       }
     }
     DTL(14);
-    // q: mean part from the summed accumulators, max part from the registers.  The node statistics of the rows / columns
-    // this lane hands over are requested first, all at once (a read-modify-write per element would be a chain of
-    // dependent round trips)
+    // hand-over of sum_t tour_emb[t] (accumulator columns 256..511) and max_t tour_emb[t] (registers) through the rows
+    // st.dgbar[:, 0] / [:, 1] (free until phase C); stage A adds the node statistics when it builds its operand tiles
     const int lbuf = (n_t - 1) & 1;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {            // max part first: it releases the registers of the running maximum
-      float4 nx[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int row = q4 * 32 + 4 * j + (lane >> 3), col = cg * 64 + c * 32 + 4 * (lane & 7);
-        nx[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (b0 + row < bs) nx[j] = *reinterpret_cast<const float4*>(st.dq + (size_t)(b0 + row) * 512 + 256 + col);
-      }
+    for (int c = 0; c < 2; ++c) {
       uint32_t raw[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(mx[c * 32 + j]);
-      coop_block(lbuf, raw, cg * 64 + c * 32, [&](int j, int row, int col, float4 x) {
-        if (b0 + row < bs)
-          *reinterpret_cast<float4*>(st.dq + (size_t)(b0 + row) * 512 + 256 + col) =
-              make_float4(nx[j].x + x.x, nx[j].y + x.y, nx[j].z + x.z, nx[j].w + x.w);
+      coop_block(lbuf, raw, cg * 64 + c * 32, [&](int, int row, int col, float4 x) {
+        if (b0 + row < bs) *reinterpret_cast<float4*>(st.dgbar + (size_t)(b0 + row) * 1024 + 256 + col) = x;
       });
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float4 nm[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int row = q4 * 32 + 4 * j + (lane >> 3), col = cg * 64 + c * 32 + 4 * (lane & 7);
-        nm[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (b0 + row < bs) nm[j] = *reinterpret_cast<const float4*>(st.dq + (size_t)(b0 + row) * 512 + col);
-      }
-      uint32_t raw[32];
       tmem_ld32_nowait(ta + 256u + (uint32_t)(cg * 64 + c * 32), raw);
       tmem_wait_ld();
-      coop_block(lbuf, raw, cg * 64 + c * 32, [&](int j, int row, int col, float4 x) {
-        // same operation order as the fused kernel: nmean + sum / K
-        if (b0 + row < bs)
-          *reinterpret_cast<float4*>(st.dq + (size_t)(b0 + row) * 512 + col) =
-              make_float4(nm[j].x + x.x / (float)K, nm[j].y + x.y / (float)K, nm[j].z + x.z / (float)K, nm[j].w + x.w / (float)K);
+      coop_block(lbuf, raw, cg * 64 + c * 32, [&](int, int row, int col, float4 x) {
+        if (b0 + row < bs) *reinterpret_cast<float4*>(st.dgbar + (size_t)(b0 + row) * 1024 + col) = x;
       });
     }
     tc_fence_before();
   }
   DTL(15);
   __threadfence_block();
-  __syncthreads();               // st.dq / st.dte rows of this tile are visible to every warp of the CTA
+  __syncthreads();               // the scratch rows and st.dte of this tile are visible to every warp of the CTA
   DTL(1);
   DTL(2);
 
   // ================================================================ stage A: ctxt (TMEM columns 0..255)
-  // (A data requested two items ahead: a load has one whole item to arrive)
+  // policy.py:179-182: q = [mean_n(node_emb) + mean_t(tour_emb), max_n(node_emb) + max_t(tour_emb)], built while the
+  // operand tiles are filled: node statistics from st.dq (GNN kernel), tour part from stage T; same operation order as
+  // the fused kernel (nmean + sum / K, nmax + max).  A data is requested two items ahead.
   {
-    float4 va[4], vb[4];
-    load_global(va, st.dq, 512, 0);
-    load_global(vb, st.dq, 512, 64);
+    // (the sums are formed when the tile is written, not when the loads are issued: the loads of two items stay in flight)
+    auto load_q = [&](float4 (&n)[4], float4 (&t)[4], int kb) {
+      const int part = kb >> 2, col = (kb & 3) * 64 + (tid & 15) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = j * 32 + (tid >> 4);
+        n[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        t[j] = n[j];
+        if (b0 + r < bs) {
+          n[j] = *reinterpret_cast<const float4*>(st.dq + (size_t)(b0 + r) * 512 + part * 256 + col);
+          t[j] = *reinterpret_cast<const float4*>(st.dgbar + (size_t)(b0 + r) * 1024 + part * 256 + col);
+        }
+      }
+    };
+    auto store_q = [&](int i, int kb, const float4 (&n)[4], const float4 (&t)[4]) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[j] = kb < 4 ? make_float4(n[j].x + t[j].x / (float)K, n[j].y + t[j].y / (float)K, n[j].z + t[j].z / (float)K, n[j].w + t[j].w / (float)K)
+                      : make_float4(n[j].x + t[j].x, n[j].y + t[j].y, n[j].z + t[j].z, n[j].w + t[j].w);
+      store_tile(i, v);
+    };
+    float4 na[4], ta4[4], nb[4], tb4[4];
+    load_q(na, ta4, 0);
+    load_q(nb, tb4, 1);
 #pragma unroll 1
     for (int kb = 0; kb < 8; kb += 2) {
       const int i = n_t + kb;
       wait_item(i - 2);
-      store_tile(i, va);
+      store_q(i, kb, na, ta4);
       issue_item(i, 0u, idesc256, kb == 0);
-      if (kb + 2 < 8) load_global(va, st.dq, 512, (kb + 2) * 64);
+      if (kb + 2 < 8) load_q(na, ta4, kb + 2);
       wait_item(i - 1);
-      store_tile(i + 1, vb);
+      store_q(i + 1, kb + 1, nb, tb4);
       issue_item(i + 1, 0u, idesc256, false);
-      if (kb + 3 < 8) load_global(vb, st.dq, 512, (kb + 3) * 64);
+      if (kb + 3 < 8) load_q(nb, tb4, kb + 3);
     }
   }
   DTL(3);
@@ -556,9 +558,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
     *reinterpret_cast<uint4*>(sQ + (size_t)(4 + row) * DT_RSTRIDE + lane * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   };
 #pragma unroll 1
-  for (int rr = warp; rr < DT_M; rr += DT_WARPS) {
+  for (;;) {
+    // rollouts are claimed one by one: their cost varies with the number of feasible actions (1 .. A) and idle ones
+    // cost nothing, a fixed assignment leaves the slowest warp ~25 % behind the average
+    int rr = 0;
+    if (lane == 0) rr = atomicAdd(&s_next[0], 1);
+    rr = __shfl_sync(0xffffffffu, rr, 0);
     const int b = b0 + rr;
-    if (b >= bs) break;
+    if (rr >= DT_M || b >= bs) break;
     if (jampr_rollout_idle(st, b, K)) continue;
     // everything this rollout needs besides the rows is requested in one round trip: per-head glimpse queries and tour
     // embeddings (lane owns columns 8 lane .. 8 lane + 7), then the action list
@@ -791,9 +798,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
 
   // ================================================================ phase F: logits + selection per rollout
 #pragma unroll 1
-  for (int rr = warp; rr < DT_M; rr += DT_WARPS) {
+  for (;;) {
+    int rr = 0;
+    if (lane == 0) rr = atomicAdd(&s_next[1], 1);
+    rr = __shfl_sync(0xffffffffu, rr, 0);
     const int b = b0 + rr;
-    if (b >= bs) break;
+    if (rr >= DT_M || b >= bs) break;
     if (jampr_rollout_idle(st, b, K)) {
       if (lane == 0) {
         st.action[2 * (size_t)b] = 0;
