@@ -68,12 +68,13 @@ def launches(csv_path, dst, header):
 def sass_table(dst):
     lib = os.path.join(ROOT, "jampr_plus_b200", "lib", "libjampr_b200.so")
     txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-    ops = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "UTCBAR", "FFMA2", "FMUL2", "FADD2", "HMNMX2",
-           "HMUL2", "MUFU", "LDS", "STS", "LDG", "STG", "SHFL", "HADD2.F32"]
+    ops = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "UTCBAR", "HMMA", "LDSM", "LDGSTS", "FFMA2", "FMUL2",
+           "FADD2", "HMNMX2", "HMUL2", "MUFU", "LDS", "STS", "LDG", "STG", "SHFL", "HADD2.F32"]
     out = ["# cuobjdump -sass jampr_plus_b200/lib/libjampr_b200.so | per-kernel opcode counts (static instructions).",
            "# UTCHMMA = tcgen05.mma kind::f16, LDTM / STTM = tcgen05.ld / st (TMEM), UBLKCP = cp.async.bulk (copy engine, 1-D),",
            "# UTMALDG / UTMASTG = tensor-map TMA (not used: operand tiles are pre-swizzled images moved by 1-D bulk copies or",
-           "# written in place by the threads), SYNCS = mbarrier ops, FFMA2 / FMUL2 / FADD2 = packed fp32 pipe.",
+           "# written in place by the threads), SYNCS = mbarrier ops, HMMA = mma.sync (per-rollout phases of the decoder), LDSM = ldmatrix,",
+           "# LDGSTS = cp.async (16-byte asynchronous row staging), FFMA2 / FMUL2 / FADD2 = packed fp32 pipe.",
            "%-64s" % "kernel" + " ".join("%9s" % o for o in ops)]
     for f in re.split(r"\n\s*Function : ", txt)[1:]:
         name = f.split("\n", 1)[0].strip()
