@@ -61,6 +61,7 @@ struct DtArgs {
   uint64_t seed;
   int step_no;
   int decode_type;
+  int tile_rollouts;     // rollouts per CTA (<= DT_M), chosen by the launcher so that the tiles fill whole waves of the SMs
 };
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
@@ -123,8 +124,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
   const jampr_state_t& st = a.st;
   if (!jampr_step_active(st.ctl, a.step_no)) return;
   const int N = d.n_nodes, K = d.n_slots, k = d.k_nbh, A = K * k;
-  const int bs = d.n_inst * d.n_samples;
-  const int b0 = blockIdx.x * DT_M;
+  const int b0 = blockIdx.x * a.tile_rollouts;
+  // one past the last rollout of this tile: accumulator rows beyond it are padding (computed, never stored or claimed)
+  const int bs = min(d.n_inst * d.n_samples, b0 + a.tile_rollouts);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t A32 = dt_a32(A);
 
@@ -950,10 +952,20 @@ extern "C" __attribute__((visibility("default"))) int jampr_debug_dtimeline(uint
 static size_t dt_smem_bytes(const jampr_dims_t* d) { return 1024 + (size_t)dt_region_bytes(d->n_slots * d->k_nbh) + 64; }
 
 template <typename T>
-static int launch_dt(const DtArgs& a, size_t smem, cudaStream_t s) {
+static int launch_dt(DtArgs& a, size_t smem, cudaStream_t s) {
   CUDA_RET(cudaFuncSetAttribute(decoder_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int bs = a.d.n_inst * a.d.n_samples;
-  decoder_tc_kernel<T><<<(bs + DT_M - 1) / DT_M, DT_THREADS, smem, s>>>(a);
+  // One CTA per SM: 128-rollout tiles would need ceil(bs / (128 n_sm)) waves with the last one partly empty (3.46 waves at
+  // 65,536 rollouts on 148 SMs).  The same number of waves is filled evenly with slightly smaller tiles (111 rollouts):
+  // the GEMM stages still run M = 128, but the per-rollout phases, two thirds of a tile's time, shrink with the tile.
+  int dev = 0, n_sm = 0;
+  CUDA_RET(cudaGetDevice(&dev));
+  CUDA_RET(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  const int waves = (bs + DT_M * n_sm - 1) / (DT_M * n_sm);
+  int tr = (bs + waves * n_sm - 1) / (waves * n_sm);
+  tr = tr < 1 ? 1 : (tr > DT_M ? DT_M : tr);
+  a.tile_rollouts = tr;
+  decoder_tc_kernel<T><<<(bs + tr - 1) / tr, DT_THREADS, smem, s>>>(a);
   return launch_status();
 }
 
