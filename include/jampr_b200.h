@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define JAMPR_ABI_VERSION 4
+#define JAMPR_ABI_VERSION 5
 
 /* argument errors */
 #define JAMPR_E_BADARG   (-1)
@@ -101,6 +101,11 @@ typedef struct {
   const float* dist_given; /* in  (I,N,N) or NULL: caller-supplied normalised transit matrix copied into `dist`
                               instead of evaluating the DIMACS formula (e.g. a matrix computed by torch on the
                               host: MKL's vsSqrt is not correctly rounded, sqrtf on the device is) */
+  float*       h0_t;       /* out (I,32,N,4)  column-chunk-major copy of h0: element [i][c][n][e] = h0[i][n][4c+e].  The
+                              single-tile tensor-core step reads these tables with thread = node; in this layout a warp's
+                              128-bit loads cover 512 contiguous bytes instead of 32 different lines.  Written by
+                              jampr_node_encoder on the 16-bit precisions for N <= 128; required there, unused otherwise */
+  float*       static_emb_t; /* out (I,64,N,4) the same for static_emb */
 } jampr_instances_t;
 
 /* Episode state, once per ROLLOUT (bs = I*P). SoA, all arrays contiguous. */

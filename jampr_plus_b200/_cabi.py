@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # JAMPR_B200_LIB selects an instrumented side build of the same library (csrc/Makefile VARIANT=...; profiling tools only)
 LIB_PATH = os.environ.get("JAMPR_B200_LIB") or os.path.join(_HERE, "lib", "libjampr_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 ST_NO_FEASIBLE, ST_TOUR_OVERFLOW, ST_FLEET_EXHAUSTED, ST_NAN_LOGITS, ST_TW_COLLAPSE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLING = 0, 1
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
@@ -30,7 +30,8 @@ class Dims(C.Structure):
 class Instances(C.Structure):
     _fields_ = [(n, _p) for n in
                 ("coords", "demand", "tw", "service", "horizon", "dist", "ttd", "knn", "knn_w", "order",
-                 "inst_status", "static_emb", "h0", "tc_tab", "tc_dtab", "lg_h16", "lg_skip", "dist_given")]
+                 "inst_status", "static_emb", "h0", "tc_tab", "tc_dtab", "lg_h16", "lg_skip", "dist_given", "h0_t",
+                 "static_emb_t")]
 
 
 STATE_FIELDS = ("visited", "pred", "succ", "plan", "vflags", "row", "nxt", "cur", "row_last", "cap", "time", "cttd",

@@ -102,6 +102,28 @@ int jampr_tc_prepare(const jampr_dims_t* d, const jampr_instances_t* inst, int p
   return launch_status();
 }
 
+// Column-chunk-major copies of h0 / static_emb (include/jampr_b200.h: h0_t, static_emb_t), once per episode after the node
+// encoder.  The step kernel reads these tables with thread = node (accumulator row): row-major that is 32 different
+// 128-byte lines per warp load (LSU-bound: 2.1 us for h0, 4.2 us for static_emb per rollout-step), here 512 contiguous bytes.
+__global__ void tc_transpose_kernel(int N, int D4, const float4* __restrict__ src, float4* __restrict__ dst) {
+  const size_t ins = blockIdx.x;
+  const float4* s = src + ins * (size_t)N * D4;
+  float4* t = dst + ins * (size_t)N * D4;
+  for (int e = threadIdx.x; e < N * D4; e += blockDim.x) {
+    const int c = e / N, n = e - c * N;
+    t[e] = s[(size_t)n * D4 + c];
+  }
+}
+
+int jampr_tc_finish(const jampr_dims_t* d, const jampr_instances_t* inst, cudaStream_t s) {
+  if (!inst->h0_t || !inst->static_emb_t) return JAMPR_E_BADARG;
+  tc_transpose_kernel<<<d->n_inst, 256, 0, s>>>(d->n_nodes, 32, reinterpret_cast<const float4*>(inst->h0),
+                                                reinterpret_cast<float4*>(inst->h0_t));
+  tc_transpose_kernel<<<d->n_inst, 256, 0, s>>>(d->n_nodes, 64, reinterpret_cast<const float4*>(inst->static_emb),
+                                                reinterpret_cast<float4*>(inst->static_emb_t));
+  return launch_status();
+}
+
 // The same mat-vec (8 outputs per thread, one input vector) software-pipelined over batches of eight weight rows:
 // batch i+1 is in flight while batch i is consumed, and the first batch (`pre`) was requested by the caller long
 // before — the weights depend on nothing, only the input vector does.  The chain of five dependent decoder stages
@@ -368,9 +390,9 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
   // h_0 row chunk 0 (per instance, L2): requested here, used after the prologue barriers
   float4 h0v[8];
   if (fresh) {
-    const float4* src = reinterpret_cast<const float4*>(p.h0 + ((size_t)ins * N + rdx) * 128 + (tid >> 7) * 64);
+    const float4* src = reinterpret_cast<const float4*>(p.h0_t) + ((size_t)ins * 32 + (tid >> 7) * 16) * N + rdx;   // [chunk][node]
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h0v[i] = __ldg(src + i);
+    for (int i = 0; i < 8; ++i) h0v[i] = __ldg(src + (size_t)i * N);
   }
   if (tid < 4) s_cnt[tid] = 0;
   for (int e = tid; e < K * N; e += P2_THREADS) s_pos[e] = (int8_t)-1;
@@ -459,10 +481,10 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       const int col0 = ch * 64 + c * 32;
       uint32_t hv[32];
       if (r < N) {
-        const float4* src = reinterpret_cast<const float4*>(p.h0 + ((size_t)ins * N + r) * 128 + col0);
+        const float4* src = reinterpret_cast<const float4*>(p.h0_t) + ((size_t)ins * 32 + (col0 >> 2)) * N + r;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 v = (c == 0) ? h0v[i] : __ldg(src + i);
+          const float4 v = (c == 0) ? h0v[i] : __ldg(src + (size_t)i * N);
           hv[4 * i] = __float_as_uint(v.x); hv[4 * i + 1] = __float_as_uint(v.y);
           hv[4 * i + 2] = __float_as_uint(v.z); hv[4 * i + 3] = __float_as_uint(v.w);
         }
@@ -583,12 +605,13 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
     // ---- node embedding rows: ne = acc + b + static_emb -> parked 16-bit rows (+ fp32 to HBM when cached).
     // The static_emb rows come from L2: chunk c+1 is in flight while chunk c is combined; chunk 0 is requested
     // before the wait for the projection MMAs.
-    const float4* se_row = reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + min(r, N - 1)) * 256 + ch * 128);
+    // chunk i (columns 128 ch + 4 i ..) of this thread's node: [chunk][node] layout, i-th chunk at se_row[i * N]
+    const float4* se_row = reinterpret_cast<const float4*>(p.static_emb_t) + ((size_t)ins * 64 + ch * 32) * N + min(r, N - 1);
     float4 sv0[8], sv1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sv0[i] = __ldg(se_row + i);
+    for (int i = 0; i < 8; ++i) sv0[i] = __ldg(se_row + (size_t)i * N);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sv1[i] = __ldg(se_row + 8 + i);
+    for (int i = 0; i < 8; ++i) sv1[i] = __ldg(se_row + (size_t)(8 + i) * N);
     if (tid == 0) mbar_wait(bar_acc, 0u);
     __syncthreads();          // projection complete and per-tour means done: the h tiles may be overwritten
   TL(21);
@@ -620,7 +643,7 @@ __global__ void __launch_bounds__(P2_THREADS, 2) policy_step_tc2_kernel(const Pt
       }
       if (c < 2) {          // refill this buffer with the chunk two ahead: in flight during the next chunk
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = __ldg(se_row + (c + 2) * 8 + i);
+        for (int i = 0; i < 8; ++i) cur[i] = __ldg(se_row + (size_t)((c + 2) * 8 + i) * N);
       }
     }
     tc_fence_before();
@@ -1020,6 +1043,7 @@ int jampr_policy_step_tc2(const jampr_dims_t* d, const jampr_instances_t* inst, 
                           const float* uniforms, int store_cache, int split, cudaStream_t s) {
   if (d->n_nodes > 128 || d->n_slots > 4 || d->k_nbh > 127) return JAMPR_E_TOOLARGE;
   if (!w->blob_bf16 || w->n_bf16 < (int64_t)W16_END) return JAMPR_E_BADARG;
+  if (!inst->h0_t || !inst->static_emb_t) return JAMPR_E_BADARG;      // column-chunk-major tables (jampr_node_encoder)
   const int N = d->n_nodes, A = d->n_slots * d->k_nbh;
   // the parked embedding (N rows of 528 B) must fit below the decoder scratch that overlays the weight stages
   if ((size_t)N * NE16_STRIDE > 4 * (size_t)p2_tile_stride(N) + 1024) return JAMPR_E_TOOLARGE;

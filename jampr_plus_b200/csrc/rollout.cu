@@ -19,6 +19,7 @@ int jampr_decoder_tc(const jampr_dims_t*, const jampr_weights_t*, const jampr_st
 int jampr_decoder_tc_fits(const jampr_dims_t*);
 int64_t jampr_w16_elems(void);
 int jampr_tc_prepare(const jampr_dims_t*, const jampr_instances_t*, int, cudaStream_t);
+int jampr_tc_finish(const jampr_dims_t*, const jampr_instances_t*, cudaStream_t);
 int jampr_lg_node_encoder(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, cudaStream_t);
 int jampr_lg_tour_encoder(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, const jampr_state_t*,
                           int, cudaStream_t);
@@ -86,9 +87,14 @@ extern "C" int jampr_node_encoder(const jampr_dims_t* d, const jampr_instances_t
     const int rc2 = jampr_tc_prepare(d, inst, w->precision, (cudaStream_t)stream);
     if (rc2) return rc2;
   }
+  int rc3;
   if (w->precision != JAMPR_PREC_F32 && (d->n_nodes > JAMPR_TILE_NODES || !ne_fp32))
-    return jampr_lg_node_encoder(d, inst, w, (cudaStream_t)stream);
-  return jampr_node_encoder_f32(d, inst, w->blob, (cudaStream_t)stream);
+    rc3 = jampr_lg_node_encoder(d, inst, w, (cudaStream_t)stream);
+  else
+    rc3 = jampr_node_encoder_f32(d, inst, w->blob, (cudaStream_t)stream);
+  // single-tile tensor-core step: column-chunk-major copies of h0 / static_emb (include/jampr_b200.h)
+  if (rc3 == 0 && w->precision != JAMPR_PREC_F32 && d->n_nodes <= JAMPR_TILE_NODES) rc3 = jampr_tc_finish(d, inst, (cudaStream_t)stream);
+  return rc3;
 }
 
 extern "C" int jampr_tour_encoder(const jampr_dims_t* d, const jampr_instances_t* inst, const jampr_weights_t* w,

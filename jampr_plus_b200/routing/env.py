@@ -339,6 +339,9 @@ class RPEnv:
             self._inst_status = ta.zeros((I,), torch.int32, dev, "inst_status")
             self._static_emb = ta.zeros((I, N, 256), torch.float32, dev, "static_emb")
             self._h0 = ta.zeros((I, N, 128), torch.float32, dev, "h0")
+            # column-chunk-major copies read by the single-tile tensor-core step (include/jampr_b200.h)
+            self._h0_t = ta.zeros((I, 32, N, 4), torch.float32, dev, "h0_t") if N <= 128 else None
+            self._static_emb_t = ta.zeros((I, 64, N, 4), torch.float32, dev, "static_emb_t") if N <= 128 else None
             # packed edge tables of the tensor-core policy step (filled by jampr_node_encoder)
             self._tc_tab = ta.zeros((I, N, (k + 3) // 4 * 4), torch.int32, dev, "tc_tab")
             self._tc_dtab = ta.zeros((I, (N + 7) // 8 * 8), torch.int32, dev, "tc_dtab")
@@ -356,7 +359,8 @@ class RPEnv:
                         ("dist", self._dist_mat), ("ttd", self.time_to_depot), ("knn", self._knn),
                         ("knn_w", self._knn_w), ("order", self.ordered_idx), ("inst_status", self._inst_status),
                         ("static_emb", self._static_emb), ("h0", self._h0), ("tc_tab", self._tc_tab),
-                        ("tc_dtab", self._tc_dtab), ("lg_h16", self._lg_h16), ("lg_skip", self._lg_skip)):
+                        ("tc_dtab", self._tc_dtab), ("lg_h16", self._lg_h16), ("lg_skip", self._lg_skip),
+                        ("h0_t", self._h0_t), ("static_emb_t", self._static_emb_t)):
             setattr(p, name, _cabi.ptr(t))
         given = None
         if dist_mat is not None:
