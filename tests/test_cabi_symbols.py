@@ -135,4 +135,5 @@ def test_header_is_plain_c_and_cxx(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
                     "-L", lib_dir, "-ljampr_b200", f"-Wl,-rpath,{lib_dir}", "-Wno-pedantic"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert int(out[0]) == len(names) and int(out[1]) == 4
+    from jampr_plus_b200 import _cabi
+    assert int(out[0]) == len(names) and int(out[1]) == _cabi.ABI_VERSION
