@@ -15,7 +15,7 @@ import torch  # noqa: E402
 from jampr_plus_b200 import Policy, RPEnv, _cabi  # noqa: E402
 from jampr_plus_b200.weights import random_state_dict  # noqa: E402
 
-NAMES = ["stage T (tour-embedding GEMMs)", "tour embeddings + query (per rollout)", "stage A (ctxt GEMM)",
+NAMES = ["stage T (tour-embedding GEMMs, drains, query hand-over)", "(block barrier)", "stage A (query + ctxt GEMM)",
          "stage B (glimpse-key GEMMs + drains)", "phase C (glimpse per rollout)", "stage D (glimpse-value GEMMs)",
          "stage E (logit-key GEMM + drain)", "phase F (logits + selection, warp 0 only)"]
 
