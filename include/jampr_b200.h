@@ -104,8 +104,9 @@ typedef struct {
   float*       h0_t;       /* out (I,32,N,4)  column-chunk-major copy of h0: element [i][c][n][e] = h0[i][n][4c+e].  The
                               single-tile tensor-core step reads these tables with thread = node; in this layout a warp's
                               128-bit loads cover 512 contiguous bytes instead of 32 different lines.  Written by
-                              jampr_node_encoder on the 16-bit precisions for N <= 128; required there, unused otherwise */
-  float*       static_emb_t; /* out (I,64,N,4) the same for static_emb */
+                              jampr_node_encoder on the 16-bit precisions; required there.  For N > 128 (layer-wise path) the
+                              layout is (I,Npad/128,32,128,4), tile-chunk-row: [i][tile][c][r][e] = h0[i][128 tile + r][4c+e] */
+  float*       static_emb_t; /* out (I,64,N,4) the same for static_emb (N <= 128 only, NULL otherwise) */
 } jampr_instances_t;
 
 /* Episode state, once per ROLLOUT (bs = I*P). SoA, all arrays contiguous. */

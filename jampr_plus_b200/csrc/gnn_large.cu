@@ -239,7 +239,9 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_layer_kernel(const LgArgs a)
     const bool live = r < nrows;
     const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t par_saddr = smem_u32(s_par);
-    const float* skr = sk + (size_t)(row0 + (live ? r : 0)) * 128;
+    // fp32 skip operand in tile-chunk-row order: float4 ((tile * 32 + chunk) * 128 + row): thread = row accesses are
+    // contiguous across a warp (row-major they were 32 different lines per warp instruction)
+    float4* sk4 = reinterpret_cast<float4*>(sk) + (size_t)tile * 32 * 128 + r;
     float2 s2 = make_float2(0.0f, 0.0f), q2 = make_float2(0.0f, 0.0f);
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_layer_kernel(const LgArgs a)
       tmem_ld32_nowait(ta + col0, acc);
       float4 sv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sv[i] = live ? *(reinterpret_cast<const float4*>(skr + col0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; ++i) sv[i] = live ? sk4[(size_t)((col0 >> 2) + i) * 128] : make_float4(0.f, 0.f, 0.f, 0.f);
       tmem_wait_ld();
       const uint32_t pb = par_saddr + (uint32_t)col0 * 4u;
 #pragma unroll
@@ -293,7 +295,6 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_layer_kernel(const LgArgs a)
       if (live) {
         const size_t ro = (size_t)(row0 + r) * 128 + col0;
         uint4* d16 = reinterpret_cast<uint4*>(hd + ro);
-        float4* d32 = reinterpret_cast<float4*>(sk + ro);
         float4* dfin = a.hfin ? reinterpret_cast<float4*>(a.hfin + ((size_t)g * N + row0 + r) * 128 + col0) : nullptr;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_layer_kernel(const LgArgs a)
         for (int i = 0; i < 8; ++i) {
           const float4 v = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
                                        __uint_as_float(acc[4 * i + 3]));
-          d32[i] = v;
+          sk4[(size_t)((col0 >> 2) + i) * 128] = v;
           if (dfin) dfin[i] = v;
         }
       }
@@ -547,6 +548,10 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_h0_kernel(const LgArgs a) {
 }
 
 // ---- elementwise helpers -----------------------------------------------------------------------------------------
+// float index of (node u, column c) inside one graph of the tile-chunk-row skip layout
+__host__ __device__ inline size_t lg_skip_index(int u, int c) {
+  return ((((size_t)(u >> 7) * 32 + (c >> 2)) * 128) + (u & 127)) * 4 + (c & 3);
+}
 // node-encoder input: h = Linear(7,128)([coords, demand, tw, service, time to depot]) (env.py:1047-1053) -> 16-bit + fp32
 template <typename T>
 __global__ void lg_input_kernel(jampr_dims_t d, jampr_instances_t p, const float* __restrict__ w, T* __restrict__ h16,
@@ -564,23 +569,37 @@ __global__ void lg_input_kernel(jampr_dims_t d, jampr_instances_t p, const float
   x = fmaf(p.ttd[iu], __ldg(w + OFF_NE_IN_WT + 6 * 128 + c), x);
   const size_t o = ((size_t)ins * npad + u) * 128 + c;
   h16[o] = to_T<T>(x);
-  hskip[o] = x;
+  hskip[(size_t)ins * npad * 128 + lg_skip_index(u, c)] = x;
 }
 
-// tour-encoder start: every rollout starts from its instance's h0
+// tour-encoder start: every rollout starts from its instance's h0 (16-bit rows from the row-major h0, fp32 skip operand
+// from its tile-chunk-row copy h0_t: both copies are contiguous on both sides)
 template <typename T>
 __global__ void lg_start_kernel(jampr_dims_t d, jampr_instances_t p, jampr_state_t st, T* __restrict__ h16,
                                 float* __restrict__ hskip, int npad, int step_no) {
   if (!jampr_step_active(st.ctl, step_no)) return;
   const int N = d.n_nodes, g = blockIdx.y, ins = g / d.n_samples;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;       // float4 index inside the graph
+  if (e >= npad * 32) return;
+  reinterpret_cast<float4*>(hskip + (size_t)g * npad * 128)[e] =
+      __ldg(reinterpret_cast<const float4*>(p.h0_t + (size_t)ins * npad * 128) + e);
   if (e >= N * 32) return;
   const float4 v = __ldg(reinterpret_cast<const float4*>(p.h0 + (size_t)ins * N * 128) + e);
-  reinterpret_cast<float4*>(hskip + (size_t)g * npad * 128)[e] = v;
   uint2 pk;
   pk.x = as_u32(Elem<T>::from2(v.x, v.y));
   pk.y = as_u32(Elem<T>::from2(v.z, v.w));
   reinterpret_cast<uint2*>(h16 + (size_t)g * npad * 128)[e] = pk;
+}
+
+// tile-chunk-row copy of h0 for graphs of more than one tile (include/jampr_b200.h: h0_t), once per episode
+__global__ void lg_h0t_kernel(int N, int npad, const float* __restrict__ h0, float* __restrict__ h0_t) {
+  const size_t ins = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;       // float4 index inside the tile-chunk-row graph
+  if (e >= npad * 32) return;
+  const int r = e & 127, c4 = (e >> 7) & 31, tile = e >> 12, u = tile * 128 + r;
+  float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (u < N) v = __ldg(reinterpret_cast<const float4*>(h0 + (ins * N + u) * 128) + c4);
+  reinterpret_cast<float4*>(h0_t + ins * (size_t)npad * 128)[e] = v;
 }
 
 // packed kNN edges for the large path: low half = source row index, high half = 16-bit weight
@@ -625,6 +644,10 @@ static int lg_node_encoder_t(const jampr_dims_t* d, const jampr_instances_t* ins
   lg_proj_kernel<T><<<dim3(nt, I), LG_THREADS, LG_PROJ_SMEM, s>>>(a, inst->static_emb, nullptr);
   a.img = IMG_NE_BASE + 16; a.bias_off = OFF_TE_IN_B;
   lg_h0_kernel<T><<<dim3(nt, I), LG_THREADS, LG_H0_SMEM, s>>>(a);
+  if (N > 128) {
+    if (!inst->h0_t) return JAMPR_E_BADARG;
+    lg_h0t_kernel<<<dim3((npad * 32 + 255) / 256, I), 256, 0, s>>>(N, npad, inst->h0, inst->h0_t);
+  }
   return launch_status();
 }
 
@@ -636,7 +659,7 @@ static int lg_tour_encoder_t(const jampr_dims_t* d, const jampr_instances_t* ins
   T* buf1 = buf0 + (size_t)bs * npad * 128;
   CUDA_RET(cudaFuncSetAttribute(lg_layer_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_LAYER_SMEM));
   CUDA_RET(cudaFuncSetAttribute(lg_proj_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_PROJ_SMEM));
-  lg_start_kernel<T><<<dim3((N * 32 + 255) / 256, bs), 256, 0, s>>>(*d, *inst, *st, buf0, st->hskip, npad, step_no);
+  lg_start_kernel<T><<<dim3((npad * 32 + 255) / 256, bs), 256, 0, s>>>(*d, *inst, *st, buf0, st->hskip, npad, step_no);
   LgArgs a;
   a.d = *d; a.p = *inst; a.st = *st; a.w = w->blob; a.w16 = w->blob_bf16;
   a.tab_shift = N > 128 ? 0 : 7;
@@ -674,7 +697,7 @@ int jampr_lg_tour_encoder(const jampr_dims_t* d, const jampr_instances_t* inst, 
                           const jampr_state_t* st, int step_no, cudaStream_t s) {
   const int rc = lg_check(d, w);
   if (rc) return rc;
-  if (!st || !st->hbuf || !st->hskip || !st->stats_part || !st->h_fin || !st->ne || !st->ne_stats) return JAMPR_E_BADARG;
+  if (!st || !st->hbuf || !st->hskip || !st->stats_part || !st->h_fin || !st->ne || !st->ne_stats || !inst->h0_t) return JAMPR_E_BADARG;
   return w->precision == JAMPR_PREC_F16 ? lg_tour_encoder_t<__half>(d, inst, w, st, step_no, s)
                                         : lg_tour_encoder_t<__nv_bfloat16>(d, inst, w, st, step_no, s);
 }

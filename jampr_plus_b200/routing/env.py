@@ -340,7 +340,7 @@ class RPEnv:
             self._static_emb = ta.zeros((I, N, 256), torch.float32, dev, "static_emb")
             self._h0 = ta.zeros((I, N, 128), torch.float32, dev, "h0")
             # column-chunk-major copies read by the single-tile tensor-core step (include/jampr_b200.h)
-            self._h0_t = ta.zeros((I, 32, N, 4), torch.float32, dev, "h0_t") if N <= 128 else None
+            self._h0_t = ta.zeros((I, 32, N, 4) if N <= 128 else (I, (N + 127) // 128, 32, 128, 4), torch.float32, dev, "h0_t")
             self._static_emb_t = ta.zeros((I, 64, N, 4), torch.float32, dev, "static_emb_t") if N <= 128 else None
             # packed edge tables of the tensor-core policy step (filled by jampr_node_encoder)
             self._tc_tab = ta.zeros((I, N, (k + 3) // 4 * 4), torch.int32, dev, "tc_tab")
