@@ -266,9 +266,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const DtArgs 
       tc_fence_after();
       const uint32_t ah = a_addr + (uint32_t)(i & 1) * 32768u, al = ah + 16384u;
       const uint32_t bh = b_addr + (uint32_t)(i & 1) * 65536u, bl = bh + 32768u;
-#ifdef JAMPR_DT_NKS1
-      nks = 1;          // timing experiment: a quarter of the MMA work (results are wrong)
-#endif
       for (int ks = 0; ks < nks; ++ks) {
         const uint64_t dah = umma_desc_sw128(ah + ks * 32), dal = umma_desc_sw128(al + ks * 32);
         const uint64_t dbh = umma_desc_sw128(bh + ks * 32), dbl = umma_desc_sw128(bl + ks * 32);
