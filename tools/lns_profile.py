@@ -4,7 +4,7 @@
 -> Python destructor -> import_sol).  Phases are bracketed by device synchronisation, so each figure is host + device
 time of that phase.
 
-    python tools/lns_profile.py [iterations]"""
+    python tools/lns_profile.py [iterations] [sub-problems per iteration = 20]"""
 import os
 import sys
 import time
@@ -21,8 +21,9 @@ from jampr_plus_b200.weights import random_state_dict  # noqa: E402
 
 warnings.simplefilter("ignore")
 n_it = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+n_sub = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 inst = read_solomon(os.path.join(ROOT, "tests", "data", "c103.txt"))
-env = RPEnv(max_concurrent_vehicles=3, k_nbh_frac=0.25, pomo=True, num_samples=20, inference=True,
+env = RPEnv(max_concurrent_vehicles=3, k_nbh_frac=0.25, pomo=True, num_samples=n_sub, inference=True,
             tour_graph_update_step=2, device="cuda")
 pol = Policy(RPEnv.OBSERVATION_SPACE, device="cuda", precision="fp16")
 pol.load_state_dict(random_state_dict(0))
@@ -42,7 +43,8 @@ def timed(name, fn):
 
 
 def report(title, tot):
-    print(f"{title}: {tot:.3f} s for {n_it} iterations ({1e3 * tot / n_it:.2f} ms each)")
+    print(f"{title}: {tot:.3f} s for {n_it} iterations of {n_sub} sub-problems ({1e3 * tot / n_it:.2f} ms each, "
+          f"{n_it * n_sub / tot:.0f} repairs/s)")
     for k, v in sorted(T.items(), key=lambda kv: -kv[1]):
         print(f"  {k:14s} {1e3 * v / n_it:7.3f} ms  {100 * v / tot:5.1f} %")
     print(f"  {'(untimed)':14s} {1e3 * (tot - sum(T.values())) / n_it:7.3f} ms")
