@@ -1,10 +1,13 @@
-// Split decoder of the tensor-core policy step (sm_100a): attn_decoder.py:62-98 + policy.py:203-227 for 128 rollouts
-// per CTA.  policy_tc2.cu (split mode) leaves per rollout the 16-bit node-embedding rows (st.ne16), their column mean /
-// max (st.dq), the per-tour means of h and the tour features (st.dqp) in HBM; this kernel runs
+// Split decoder of the tensor-core policy step (sm_100a): tour_encoder.py:202-213, policy.py:179-182, attn_decoder.py:62-98
+// and policy.py:203-227 for up to 128 rollouts per CTA.  policy_tc2.cu (split mode) leaves per rollout the 16-bit
+// node-embedding rows (st.ne16), their column mean / max (st.dq), the per-tour means of h and the tour features (st.dqp)
+// in HBM; this kernel runs
 //
-//   stage T   tour_emb[t] (per-tour-mean half) = mean_h[t] W_to2^T      K x GEMM 128 x 256 x 128   (tour_encoder.py:202-213)
-//             + per rollout: feature half, query q = [mean + mean, max + max]                   (policy.py:179-182)
-//   stage A   ctxt = q W_c^T                       GEMM 128 x 256 x 512          (attn_decoder.py:73)
+//   stage T   tour_emb[t] = W_to [input_proj(f_t) | mean_h[t]] + b as one product over K = 192 per vehicle slot (mean half,
+//             then [features, 1]: feature matrix and bias folded into the third B tile); a second set of accumulator
+//             columns collects sum_t, the running max_t stays in registers                       (tour_encoder.py:202-213)
+//   stage A   q = [mean_n + mean_t, max_n + max_t] formed while the tiles are filled (policy.py:179-182);
+//             ctxt = q W_c^T                       GEMM 128 x 256 x 512          (attn_decoder.py:73)
 //   stage B   qp_h = W_gk,h^T ctxt_h  (4 heads)    4 GEMMs 128 x 256 x 64        (set_proj moved to the query side)
 //   phase C   per rollout, one warp: glimpse scores qp_h . (node_emb[n_a] + tour_emb[t_a]) over the FEASIBLE actions,
 //             masked softmax per head, gbar_h = sum_a p_h[a] act[a] — on warp-level tensor-core MMAs (see below)
@@ -17,10 +20,11 @@
 // a lo 16-bit part (x = hi + lo) and every K step issues hi*hi + lo*hi + hi*lo: ~21 significand bits, i.e. the stages
 // are as accurate as fp32 mat-vecs.  That matters: the glimpse scores are O(10) before the softmax, and rounding the
 // glimpse-key weights alone to fp16 costs 9e-3 in the log-probabilities (tools/emulate_tc_precision.py).  The tensor
-// pipe has the room: 0.85 MFLOP per rollout x 3 is 5 % of the GNN's MMAs.  Weights are read once per 128 rollouts
+// pipe has the room: 1.0 MFLOP per rollout x 3 is 6 % of the GNN's MMAs.  Weights are read once per tile
 // (the fused per-rollout decoder streamed 704 KB of them per rollout).
 // A operand tiles are written by the threads (from HBM vectors or straight from the previous accumulator in TMEM),
-// B tiles are pre-swizzled images streamed by the bulk-copy engine into a double buffer, one item ahead.
+// B tiles are pre-swizzled images streamed by the bulk-copy engine; both are double-buffered and two items are in flight.
+// A tile holds ceil(bs / (waves x SMs)) <= 128 rollouts, so that the one-CTA-per-SM grid runs whole waves.
 //
 // The per-rollout phases C and F are the HBM-facing part: each gathers the 16-bit node-embedding rows of the feasible
 // actions (512 B per row, ~2.7 GB per launch at 65,536 rollouts).  A warp stages 16 rows at a time in shared memory
@@ -29,7 +33,7 @@
 //   scores   S[h][a]  = sum_c Qp[h][c] R[a][c]     A = Qp as [hi(4 heads); lo(4 heads)] (fp32 = hi + lo), B = R
 //   glimpse  G[c][h] += sum_a R[a][c] P[a][h]      A = R^T (ldmatrix.trans), B = [hi(p); lo(p)] straight from the score
 //                                                  accumulators (flash-attention register reuse), online softmax
-// so the rows are fetched once for scores and weighted sums, and a rollout costs ~2.5 k instructions instead of
+// so the rows are fetched once for scores and weighted sums, and a rollout costs ~5.6 k instructions instead of
 // ~12 k on the CUDA cores.  Node-embedding rows are exact 16-bit values; queries and probabilities enter as hi + lo,
 // products are exact and accumulate in fp32: the accuracy of the fp32 dot products it replaces.
 #include <stdlib.h>
@@ -41,7 +45,7 @@
 #define DT_RROWS 16            // node-embedding rows staged per chunk (two mma n-tiles)
 #define DT_RSTRIDE 528         // bytes per staged row: 512 + 16 (8 consecutive rows hit 32 distinct banks in ldmatrix)
 #define DT_GSTRIDE 260         // floats per row of the [8][256] hand-over of the glimpse accumulators (conflict-free)
-#define DT_ITEMS 32            // B tiles consumed after stage T (2 per vehicle slot): 8 (stage A) + 4 (B) + 16 (D) + 4 (E)
+#define DT_ITEMS 32            // B tiles consumed after stage T (3 per vehicle slot): 8 (stage A) + 4 (B) + 16 (D) + 4 (E)
 
 // per-phase time line of the CTAs (tools/timeline.py decoder): build with `make EXTRA=-DJAMPR_TIMELINE`
 #ifdef JAMPR_TIMELINE
