@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_layer_kernel(const LgArgs a)
 // out (N x 256) = h W^T + bias (+ static_emb): A = own h rows (K-blocks 2,3 of the tile layout), B = four stages
 // (rows 0..127 x K-blocks 0,1, then rows 128..255).  mode 0 also reduces column sum / max over the tile's rows.
 template <typename T>
-__global__ void __launch_bounds__(LG_THREADS, 2) lg_proj_kernel(const LgArgs a, float* __restrict__ out, float* __restrict__ stats_part) {
+__global__ void __launch_bounds__(LG_THREADS, 2) lg_proj_kernel(const LgArgs a, float* __restrict__ out, float* __restrict__ stats_part,
+                                                                T* __restrict__ out16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const jampr_dims_t& d = a.d;
   const jampr_instances_t& p = a.p;
@@ -392,32 +393,45 @@ __global__ void __launch_bounds__(LG_THREADS, 2) lg_proj_kernel(const LgArgs a, 
   }
   __syncthreads();
   tc_fence_after();
-  const int q = warp & 3, ch = warp >> 2, r = q * 32 + lane;
+  // Epilogue.  tcgen05.ld hands a thread 32 columns of ITS row; loading static_emb and storing the rows from there would
+  // be 32 different 128-byte lines per warp instruction (LSU-bound).  Each warp turns its 32 x 32 block through 4 KB of
+  // shared memory (the operand tiles are dead; 16-byte chunks XOR-ed with the row: conflict-free both ways), after
+  // which 8 lanes cover 128 contiguous bytes of one row for the static_emb load and the fp32 / 16-bit stores.
+  const int q = warp & 3, ch = warp >> 2;
   const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16);
-  const int u = row0 + r;
-  float* orow = out + ((size_t)g * N + (r < nrows ? u : 0)) * 256;
+  uint8_t* tt = sA + (size_t)warp * 4096;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const int col0 = ch * 128 + c * 32;
     uint32_t acc[32];
     tmem_ld32_nowait(ta + col0, acc);
     tmem_wait_ld();
-    if (r < nrows) {
-      const float4* bo = reinterpret_cast<const float4*>(a.w + a.bias_off + col0);
-      const float4* se = reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + u) * 256 + col0);
-      float4* dst = reinterpret_cast<float4*>(orow + col0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b4 = __ldg(bo + i);
-        float4 v = make_float4(__uint_as_float(acc[4 * i]) + b4.x, __uint_as_float(acc[4 * i + 1]) + b4.y,
-                               __uint_as_float(acc[4 * i + 2]) + b4.z, __uint_as_float(acc[4 * i + 3]) + b4.w);
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<uint4*>(tt + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    __syncwarp();
+    const int cc = lane & 7, col = col0 + 4 * cc;
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.w + a.bias_off + col));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rw = 4 * j + (lane >> 3), r = q * 32 + rw;
+      if (r < nrows) {
+        const uint4 x = *reinterpret_cast<const uint4*>(tt + rw * 128 + ((cc ^ (rw & 7)) << 4));
+        float4 v = make_float4(__uint_as_float(x.x) + b4.x, __uint_as_float(x.y) + b4.y, __uint_as_float(x.z) + b4.z,
+                               __uint_as_float(x.w) + b4.w);
+        const size_t u = (size_t)row0 + r;
         if (a.mode == 0) {
-          const float4 s4 = __ldg(se + i);
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + u) * 256 + col));
           v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
         }
-        dst[i] = v;
+        *reinterpret_cast<float4*>(out + ((size_t)g * N + u) * 256 + col) = v;
+        // 16-bit copy of the rows for the 128-rollout decoder (decoder_tc.cu gathers the candidate rows from it)
+        if (out16)
+          *reinterpret_cast<uint2*>(out16 + ((size_t)g * N + u) * 256 + col) =
+              make_uint2(as_u32(Elem<T>::from2(v.x, v.y)), as_u32(Elem<T>::from2(v.z, v.w)));
       }
     }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -641,7 +655,7 @@ static int lg_node_encoder_t(const jampr_dims_t* d, const jampr_instances_t* ins
     T* t = src; src = dst; dst = t;
   }
   a.h_src = src; a.img = IMG_NE_BASE + 12;
-  lg_proj_kernel<T><<<dim3(nt, I), LG_THREADS, LG_PROJ_SMEM, s>>>(a, inst->static_emb, nullptr);
+  lg_proj_kernel<T><<<dim3(nt, I), LG_THREADS, LG_PROJ_SMEM, s>>>(a, inst->static_emb, nullptr, nullptr);
   a.img = IMG_NE_BASE + 16; a.bias_off = OFF_TE_IN_B;
   lg_h0_kernel<T><<<dim3(nt, I), LG_THREADS, LG_H0_SMEM, s>>>(a);
   if (N > 128) {
@@ -674,8 +688,42 @@ static int lg_tour_encoder_t(const jampr_dims_t* d, const jampr_instances_t* ins
     T* t = src; src = dst; dst = t;
   }
   a.h_src = src; a.img = 24; a.hfin = nullptr;
-  lg_proj_kernel<T><<<dim3(nt, bs), LG_THREADS, LG_PROJ_SMEM, s>>>(a, st->ne, st->stats_part);
+  lg_proj_kernel<T><<<dim3(nt, bs), LG_THREADS, LG_PROJ_SMEM, s>>>(a, st->ne, st->stats_part, reinterpret_cast<T*>(st->ne16));
   lg_stats_kernel<<<bs, 256, 0, s>>>(*d, *st, st->stats_part, nt, step_no);
+  return launch_status();
+}
+
+// Hand-over of the layer-wise path to the 128-rollout decoder (decoder_tc.cu), every step: node statistics -> st.dq,
+// per-tour means of h over buffer positions 0..idx (one depot entry included, tour_encoder.py:236-243) and the tour
+// features (env.py:1061-1068) -> st.dqp; the 16-bit node-embedding rows were written by lg_proj_kernel on the last fresh step.
+__global__ void __launch_bounds__(128) lg_handover_kernel(jampr_dims_t d, jampr_state_t st, int step_no) {
+  if (!jampr_step_active(st.ctl, step_no)) return;
+  const int b = blockIdx.x, K = d.n_slots, N = d.n_nodes, L = d.plan_len, c = threadIdx.x;
+  if (jampr_rollout_idle(st, b, K)) return;
+  for (int e = c; e < 512; e += 128) st.dq[(size_t)b * 512 + e] = st.ne_stats[(size_t)b * 512 + e];
+  const float* hf = st.h_fin + (size_t)b * N * 128;
+  for (int t = 0; t < K; ++t) {
+    const size_t bk = (size_t)b * K + t;
+    const int row = st.row[bk];
+    const int16_t* pr = st.plan + ((size_t)b * d.k_max + row) * L;
+    int idx = 0;
+    while (idx < L && pr[idx] != 0) ++idx;
+    if (idx >= L) idx = 0;                       // argmin over an all-nonzero row is position 0
+    float sum = hf[(size_t)pr[0] * 128 + c];
+    for (int q = 1; q <= idx; ++q) sum += hf[(size_t)pr[q] * 128 + c];
+    float* o = st.dqp + ((size_t)b * 4 + t) * 256;
+    o[c] = sum / (float)(idx + 1);
+    if (c < 5) {
+      const float f = c == 0 ? (float)st.cur[bk] : c == 1 ? st.cap[bk] : c == 2 ? st.time[bk] : c == 3 ? st.cttd[bk]
+                                                                                 : (float)(d.k_max - row) / (float)d.k_max;
+      o[128 + c] = f;
+    }
+  }
+}
+
+int jampr_lg_handover(const jampr_dims_t* d, const jampr_state_t* st, int step_no, cudaStream_t s) {
+  if (!st->dq || !st->dqp || !st->h_fin || !st->ne_stats) return JAMPR_E_BADARG;
+  lg_handover_kernel<<<d->n_inst * d->n_samples, 128, 0, s>>>(*d, *st, step_no);
   return launch_status();
 }
 

@@ -23,6 +23,7 @@ int jampr_tc_finish(const jampr_dims_t*, const jampr_instances_t*, cudaStream_t)
 int jampr_lg_node_encoder(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, cudaStream_t);
 int jampr_lg_tour_encoder(const jampr_dims_t*, const jampr_instances_t*, const jampr_weights_t*, const jampr_state_t*,
                           int, cudaStream_t);
+int jampr_lg_handover(const jampr_dims_t*, const jampr_state_t*, int, cudaStream_t);
 #define JAMPR_TILE_NODES 128     // graphs up to this size run the single-tile kernels, larger ones the layer-wise path
 
 // Tensor-core policy step, variant per jampr_weights_t.tc_variant (include/jampr_b200.h): 3 = the two-CTAs-per-SM GNN
@@ -121,10 +122,16 @@ extern "C" int jampr_policy_step(const jampr_dims_t* d, const jampr_instances_t*
   if (!st->h_fin || !st->ne || !st->ne_stats) return JAMPR_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (w->precision != JAMPR_PREC_F32 && d->n_nodes > JAMPR_TILE_NODES) {
-    // large-graph path: layer-wise tensor-core GNN through HBM/L2, then the fp32 decoder kernel
+    // large-graph path: layer-wise tensor-core GNN through HBM/L2; then the tcgen05 decoder over tiles of rollouts when
+    // the caller supplied its hand-over buffers and the action set fits (decoder_tc.cu), else the fp32 decoder kernel
     if (graph_fresh) {
       rc = jampr_lg_tour_encoder(d, inst, w, st, step_no, s);
       if (rc) return rc;
+    }
+    if (st->ne16 && st->dq && st->dte && st->dqp && st->dgbar && st->dlp && jampr_decoder_tc_fits(d)) {
+      rc = jampr_lg_handover(d, st, step_no, s);
+      if (rc) return rc;
+      return jampr_decoder_tc(d, w, st, step_no, decode_type, seed, uniforms, s);
     }
     return jampr_decoder_launch(d, inst, st, w->blob, step_no, decode_type, seed, uniforms, s);
   }

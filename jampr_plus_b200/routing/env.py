@@ -94,7 +94,7 @@ _POLICY_SPEC = {
     "ne_stats": (torch.float32, lambda s: (s.bs, 2, 256)),
 }
 # split decoder of the tensor-core path (csrc/decoder_tc.cu): hand-over buffers between the per-rollout GNN kernel and
-# the 128-rollouts-per-CTA decoder kernel; allocated when a 16-bit policy drives a graph that fits one tile
+# the 128-rollouts-per-CTA decoder kernel; allocated when a 16-bit policy drives the env (up to four concurrent vehicles)
 _SPLIT_SPEC = {
     "ne16": (torch.int16, lambda s: (s.bs, s.N, 256)),
     "dq": (torch.float32, lambda s: (s.bs, 512)),
@@ -127,7 +127,7 @@ class DeviceState:
 
     def ensure_policy_buffers(self, want_logp: bool = False, split: bool = False):
         changed = False
-        if split and self.N <= 128 and self.K <= 4:
+        if split and self.K <= 4:      # (graphs of several tiles: the layer-wise GNN feeds the same decoder)
             for name, (dt, shp) in _SPLIT_SPEC.items():
                 if name not in self.t:
                     self.t[name] = self._alloc.zeros(shp(self), dt, self.device, name)
