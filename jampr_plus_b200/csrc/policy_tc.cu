@@ -380,10 +380,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
     {
       uint32_t hv[32];
       if (r < N) {
-        const float4* src = reinterpret_cast<const float4*>(p.h0 + ((size_t)ins * N + r) * 128 + cg * 32);
+        // column-chunk-major copy (include/jampr_b200.h h0_t): contiguous across the warp's nodes
+        const float4* src = reinterpret_cast<const float4*>(p.h0_t) + ((size_t)ins * 32 + cg * 8) * N + r;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 v = __ldg(src + i);
+          const float4 v = __ldg(src + (size_t)i * N);
           hv[4 * i] = __float_as_uint(v.x); hv[4 * i + 1] = __float_as_uint(v.y);
           hv[4 * i + 2] = __float_as_uint(v.z); hv[4 * i + 3] = __float_as_uint(v.w);
         }
@@ -507,13 +508,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_step_tc_kernel(const PtA
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int c0 = hf * 128 + cg * 32;
-        const float4* se = reinterpret_cast<const float4*>(p.static_emb + ((size_t)ins * N + r) * 256 + c0);
+        const float4* se = reinterpret_cast<const float4*>(p.static_emb_t) + ((size_t)ins * 64 + (c0 >> 2)) * N + r;   // [chunk][node]
         const float4* bo = reinterpret_cast<const float4*>(w + OFF_TE_OUT_B + c0);
         float4* dst = reinterpret_cast<float4*>(s_ne + (size_t)r * NE_STRIDE + c0);
         float4* gdst = a.store_cache ? reinterpret_cast<float4*>(st.ne + ((size_t)b * N + r) * 256 + c0) : nullptr;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 s4 = __ldg(se + i), b4 = __ldg(bo + i);
+          const float4 s4 = __ldg(se + (size_t)i * N), b4 = __ldg(bo + i);
           const uint32_t* ac = hf ? acc1 : acc0;
           const float4 v = make_float4(__uint_as_float(ac[4 * i]) + b4.x + s4.x, __uint_as_float(ac[4 * i + 1]) + b4.y + s4.y,
                                        __uint_as_float(ac[4 * i + 2]) + b4.z + s4.z, __uint_as_float(ac[4 * i + 3]) + b4.w + s4.w);
@@ -836,6 +837,7 @@ int jampr_policy_step_tc(const jampr_dims_t* d, const jampr_instances_t* inst, c
                          const float* uniforms, int store_cache, cudaStream_t s) {
   if (d->n_nodes > 128 || d->n_slots > 4 || d->k_nbh > 127) return JAMPR_E_TOOLARGE;
   if (!w->blob_bf16 || w->n_bf16 < (int64_t)W16_END) return JAMPR_E_BADARG;
+  if (!inst->h0_t || !inst->static_emb_t) return JAMPR_E_BADARG;      // column-chunk-major tables (jampr_node_encoder)
   const size_t smem = pt_smem_bytes(d);
   if (smem > 227 * 1024) return JAMPR_E_TOOLARGE;
   PtArgs a;
